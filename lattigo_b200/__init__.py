@@ -1,0 +1,6 @@
+"""lattigo_b200 -- B200-native (sm_100a) RNS polynomial-ring engine behind Lattigo's `ring` /
+`rlwe.Evaluator` hot-path interface. The compute lives in csrc/ (hand-written CUDA + C ABI,
+include/lattigo_b200.h); this package is the thin host-side mirror of the reference's method names
+used by the tests and the benchmark. No CPU fallback exists."""
+from ._lib import LgpuError, lib, declared_symbols, SO_PATH  # noqa: F401
+from .ring import Context, Ring, SubRing, OPS, OP  # noqa: F401

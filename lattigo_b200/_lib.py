@@ -1,0 +1,67 @@
+"""ctypes loader for lattigo_b200/lib/liblattigo_b200.so (the C ABI in include/lattigo_b200.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing this module raises, loudly."""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "lib", "liblattigo_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "lattigo_b200.h")
+
+_lib = None
+
+
+class LgpuError(RuntimeError):
+    pass
+
+
+def declared_symbols():
+    """Every function name declared in include/lattigo_b200.h."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise LgpuError(
+                "liblattigo_b200.so is missing (%s). Build it with `python -m lattigo_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback." % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        c = ctypes
+        vp, u64, i, z = c.c_void_p, c.c_uint64, c.c_int, c.c_size_t
+        L.lgpu_last_error.restype = c.c_char_p
+        L.lgpu_version.restype = c.c_char_p
+        sig = {
+            "lgpu_create": [c.POINTER(vp), i, i, i, vp, i, vp, i],
+            "lgpu_destroy": [vp],
+            "lgpu_sync": [vp, vp],
+            "lgpu_ring_get_table": [vp, i, i, i, vp, z],
+            "lgpu_ring_set_roots": [vp, i, i, vp, vp, u64],
+            "lgpu_malloc": [vp, c.POINTER(vp), z],
+            "lgpu_free": [vp, vp],
+            "lgpu_memcpy_h2d": [vp, vp, vp, z, vp],
+            "lgpu_memcpy_d2h": [vp, vp, vp, z, vp],
+            "lgpu_ntt": [vp, i, i, vp, vp, i, i, z, vp],
+            "lgpu_intt": [vp, i, i, vp, vp, i, i, z, vp],
+            "lgpu_subring_ntt": [vp, i, i, vp, vp, i, vp],
+            "lgpu_subring_intt": [vp, i, i, vp, vp, i, vp],
+            "lgpu_vecop": [vp, i, i, i, vp, vp, vp, vp, vp, i, z, vp],
+            "lgpu_subring_vecop": [vp, i, i, i, vp, vp, vp, u64, u64, i, vp],
+        }
+        for name, args in sig.items():
+            f = getattr(L, name)
+            f.argtypes = args
+            if name != "lgpu_destroy":
+                f.restype = i
+        L.lgpu_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise LgpuError(lib().lgpu_last_error().decode())

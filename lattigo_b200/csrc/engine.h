@@ -1,0 +1,129 @@
+// engine.h -- host-side structures of the B200 RNS ring engine (C++ mirror of the reference's
+// ring.Ring / ring.BasisExtender / ring.Decomposer / rlwe.Evaluator state for the hot path).
+//
+// Data layout in HBM: a polynomial is a contiguous (limb, coeff) row-major block of uint64,
+// row stride >= N words (ring/poly.go:13-15 keeps one Go slice per limb; the cgo shim makes those
+// slices views of the rows of one such block). Batches are arrays of polynomials with a constant
+// batch stride. Constants live once per context in device memory (LimbConst table + root tables +
+// basis-extension matrices) and are addressed through a "global limb index": Q limbs 0..nQ-1 followed
+// by P limbs nQ..nQ+nP-1, so that one kernel launch can cover the Q and P parts of a ringqp.Poly.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+
+namespace lgpu {
+
+constexpr int kMaxRows = 128;  // max limbs (rows) handled by one launch
+
+// Per-limb device constants. ring/subring.go:15-35 + ring/ntt.go:38-44.
+struct LimbConst {
+    u64 q;        // Modulus
+    u64 qinv;     // MRedConstant = q^-1 mod 2^64
+    u64 bred_hi;  // BRedConstant[0]
+    u64 bred_lo;  // BRedConstant[1]
+    u64 ninv;     // NInv = MForm(N^-1 mod q)
+    const u64* roots_fwd;  // RootsForward  (device, NthRoot/2 entries)
+    const u64* roots_bwd;  // RootsBackward (device)
+};
+
+// Which global limb each row of a launch uses.
+struct RowMap {
+    int nrows;
+    unsigned char limb[kMaxRows];
+};
+
+struct HostSubRing {
+    u64 q, qinv, bred_hi, bred_lo, ninv, primitive_root;
+    std::vector<u64> roots_fwd, roots_bwd;  // host copies (also returned through the C ABI for cross-checks)
+};
+
+// ring.ModUpConstants for a (source chain, target chain) pair -- ring/basis_extension.go:90-98.
+// Device layout: qoverqiinvqi[nS] | qoverqimodp[nT][nS] | vtimesqmodp[nT][nS+1], offsets into the blob.
+struct ModUpSet {
+    int nS = 0, nT = 0;
+    size_t off_qoverqiinvqi = 0, off_qoverqimodp = 0, off_vtimesqmodp = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    int logN = 0, N = 0;
+    int ring_type = 0;  // 0 = Standard, 1 = ConjugateInvariant
+    u64 nthroot = 0;
+    int nQ = 0, nP = 0;
+    std::vector<u64> Q, P;
+    std::vector<HostSubRing> sub;  // nQ + nP (global limb index)
+    // device tables
+    LimbConst* d_limbs = nullptr;
+    u64* d_roots = nullptr;        // 2 * (nQ+nP) * (nthroot/2) words
+    std::vector<LimbConst> h_limbs;
+    // rescale constants, ring/ring.go:329-346: rescale[(j-1)*nQ + i] = MForm(q_i - q_j^-1 mod q_i)  (Q ring)
+    std::vector<u64> rescaleQ, rescaleP;
+    // basis-extension constant blob (host mirror + device)
+    std::vector<u64> h_blob;
+    u64* d_blob = nullptr;
+    std::vector<ModUpSet> muc_QtoP;  // [levelQ]: Q[:levelQ+1] -> P (all)
+    std::vector<ModUpSet> muc_PtoQ;  // [levelP]: P[:levelP+1] -> Q (all)
+    // decomposer sets, ring/basis_extension.go:333-373: index (nbPi-2, digit, decompLvl)
+    std::vector<std::vector<std::vector<ModUpSet>>> muc_dec;
+    // modDownConstants: [levelP][i] (PtoQ) and [levelQ][j] (QtoP), Montgomery form  (:25-49)
+    std::vector<u64> mdc_PtoQ, mdc_QtoP;
+    // half-moduli: floor(Q_l/2) mod q_i, mod p_j etc. are computed on the fly from prefix products
+    cudaStream_t stream = nullptr;  // default stream of the context
+    // scratch arena (device), grown on demand; used by composite ops (ModDown, GadgetProduct, ...)
+    u64* d_scratch = nullptr;
+    size_t scratch_words = 0;
+    // automorphism index cache: galEl -> device index table (u32[N])
+    std::vector<std::pair<u64, unsigned int*>> auto_index;
+};
+
+// ---- error handling --------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+const char* last_error();
+#define LGPU_CUDA_OK(expr)                                                                       \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            lgpu::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+            return -1;                                                                           \
+        }                                                                                        \
+    } while (0)
+
+// ---- host number theory (tables.cu) ------------------------------------------------------------------
+u64 h_mulmod(u64 a, u64 b, u64 m);
+u64 h_powmod(u64 a, u64 e, u64 m);
+u64 h_invmod(u64 a, u64 m);  // m prime
+bool h_is_prime(u64 n);
+u64 h_mform(u64 a, u64 q);   // a * 2^64 mod q
+int build_context(Ctx* c, int device, int logN, int ring_type, const u64* q, int nq, const u64* p, int np);
+void destroy_context(Ctx* c);
+int ensure_scratch(Ctx* c, size_t words);
+// half modulus of the product of `mods[0..n)` reduced mod m: floor(prod/2) mod m
+u64 h_half_prod_mod(const u64* mods, int n, u64 m);
+
+// ---- launchers (ntt.cu / vecops.cu / basisext.cu / keyswitch.cu) ---------------------------------------
+// All launchers are asynchronous on `st`. rows: RowMap; data: base pointer, row stride, batch count/stride.
+struct Span {
+    u64* p;
+    size_t row_stride;    // words between consecutive rows (limbs)
+    size_t batch_stride;  // words between consecutive batch elements
+};
+struct CSpan {
+    const u64* p;
+    size_t row_stride;
+    size_t batch_stride;
+};
+
+enum NttMode { NTT_CANONICAL = 0, NTT_EXACT_LAZY = 1 };
+
+int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st);
+int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st);
+
+int launch_vecop(const Ctx* c, const RowMap& rm, int op, CSpan p1, CSpan p2, Span p3, int batch,
+                 const u64* d_s0, const u64* d_s1, u64 s0, u64 s1, int n, cudaStream_t st);
+
+}  // namespace lgpu

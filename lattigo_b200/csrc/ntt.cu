@@ -1,0 +1,354 @@
+// ntt.cu -- forward / inverse negacyclic NTT over (limb, coeff) row-major uint64 polynomials.
+//
+// Replaces ring.Ring.NTT / NTTLazy / INTT / INTTLazy and the per-row SubRing forms
+// (reference: ring/ntt.go:127-152,174-206, hot loops nttUnrolled16Lazy :258-552 and
+// inttLazyUnrolled16 :608-714).
+//
+// Decomposition (N = 2^logN, one launch covers rows x batch):
+//   forward : [strided pass: first s1 = max(0, logN-12) stages, radix-2^s1 in registers, no smem]
+//             -> [chunk pass: remaining c = logN - s1 <= 12 stages on contiguous 2^c-element chunks,
+//                 radix-16 register rounds exchanged through padded shared memory]
+//   inverse : chunk pass (stages in reverse order, Gentleman-Sande) -> strided pass (+ N^-1 scaling).
+// Every element crosses HBM twice per transform when logN > 12 (the intermediate stays L2-resident for
+// working sets below ~100 MB), once when logN <= 12.
+//
+// Arithmetic: butterflies are the reference's lazy Montgomery butterflies (ring/ntt.go:155-171) with the
+// reference's own 4q-correction schedule, so NTT_EXACT_LAZY reproduces NTTLazy's representative in [0, 6q)
+// bit for bit; NTT_CANONICAL appends the BRedAdd pass (ring/ntt.go:174-177) in the store epilogue.
+#include "engine.h"
+#include "modarith.cuh"
+
+namespace lgpu {
+
+struct NttParams {
+    const LimbConst* limbs;
+    RowMap rm;
+    const u64* in;
+    u64* out;
+    size_t in_rs, in_bs, out_rs, out_bs;
+    int logN;
+    int mode;     // NttMode
+    int ci;       // conjugate-invariant ring (stage numbering differs) -- not handled by these kernels
+};
+
+// reference schedule for the forward U >= 4q correction, ring/ntt.go:275-310 (never on stage 0),
+// :318 (bits.Len64(m) odd <=> stage index even), :500-518 (always on the last stage).
+__device__ __forceinline__ bool fwd_reduce_flag(int s, int logN) { return (s == logN - 1) || (s > 0 && (s & 1) == 0); }
+
+__device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qinv, bool reduce) {
+    u64 U = X;
+    u64 fourq = q << 2;
+    if (reduce) U = (U >= fourq) ? U - fourq : U;
+    u64 V = mred_lazy(Y, psi, q, qinv);
+    X = U + V;
+    Y = U + (q << 1) - V;
+}
+// invbutterfly, ring/ntt.go:164-171
+__device__ __forceinline__ void inv_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qinv) {
+    u64 U = X, V = Y;
+    u64 twoq = q << 1;
+    u64 s = U + V;
+    X = (s >= twoq) ? s - twoq : s;
+    Y = mred_lazy(U + (q << 2) - V, psi, q, qinv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// strided pass: global stages [0, RL). Thread l handles elements {k * (N >> RL) + l}.
+// ---------------------------------------------------------------------------------------------------
+template <int RL, bool INVERSE>
+__global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
+    constexpr int R = 1 << RL;
+    const int row = blockIdx.y, b = blockIdx.z;
+    const LimbConst L = p.limbs[p.rm.limb[row]];
+    const int N = 1 << p.logN;
+    const int stride = N >> RL;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= stride) return;
+    const u64* in = p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs;
+    u64* out = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs;
+    const u64 q = L.q, qinv = L.qinv;
+    u64 x[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) x[k] = in[(size_t)k * stride + l];
+    if (!INVERSE) {
+        const u64* roots = L.roots_fwd;
+#pragma unroll
+        for (int u = 0; u < RL; u++) {
+            const int half = 1 << (RL - 1 - u);
+            const bool red = fwd_reduce_flag(u, p.logN);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                u64 tw = __ldg(roots + (1 << u) + (k >> (RL - u)));
+                fwd_bfly(x[k], x[k + half], tw, q, qinv, red);
+            }
+        }
+        if (p.mode == NTT_CANONICAL && RL == 0) {}
+    } else {
+        const u64* roots = L.roots_bwd;
+#pragma unroll
+        for (int u = RL - 1; u >= 0; u--) {
+            const int half = 1 << (RL - 1 - u);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                u64 tw = __ldg(roots + (1 << u) + (k >> (RL - u)));
+                inv_bfly(x[k], x[k + half], tw, q, qinv);
+            }
+        }
+        // x N^-1 (Montgomery), canonical: ring/ntt.go:185-206 (mulscalarmontgomeryvec, also for the Lazy API when N >= 16)
+#pragma unroll
+        for (int k = 0; k < R; k++) x[k] = mred(x[k], L.ninv, q, qinv);
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) out[(size_t)k * stride + l] = x[k];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// chunk pass: global stages [s1, logN) on a contiguous chunk of C = 2^CL elements held in shared memory.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int round_bits(int cl, int i) {
+    // radix schedule (bits per register round) for a chunk of 2^cl elements
+    return cl == 12 ? 4
+         : cl == 11 ? (i < 2 ? 4 : 3)
+         : cl == 10 ? (i < 1 ? 4 : 3)
+         : cl == 9  ? 3
+         : cl == 8  ? (i < 2 ? 4 : 0)
+         : cl == 7  ? (i == 0 ? 4 : (i == 1 ? 3 : 0))
+         : cl == 6  ? (i < 2 ? 3 : 0)
+         : cl == 5  ? (i == 0 ? 3 : (i == 1 ? 2 : 0))
+         :            (i == 0 ? 4 : 0);
+}
+__host__ __device__ constexpr int num_rounds(int cl) { return cl >= 9 ? 3 : (cl >= 5 ? 2 : 1); }
+
+__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
+
+// One register round of the forward transform on chunk-local stages [A, A+RB).
+template <int CL, int A, int RB, bool FROM_GLOBAL>
+__device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const u64* roots, u64 q, u64 qinv,
+                                          int s1, int logN, int chunk, int tid) {
+    constexpr int G = 16 >> RB;          // groups per thread
+    constexpr int RR = 1 << RB;          // elements per group
+    constexpr int LOB = CL - A - RB;     // bits of `lo`
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int g = tid * G + gi;
+        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
+        const int base = (hi << (CL - A)) + lo;
+        u64 x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) {
+            const int idx = base + (k << LOB);
+            x[k] = FROM_GLOBAL ? gsrc[idx] : sm[pad_idx(idx)];
+        }
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int half = 1 << (RB - 1 - u);
+            const int s = s1 + A + u;
+            const bool red = fwd_reduce_flag(s, logN);
+            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+#pragma unroll
+            for (int k = 0; k < RR; k++) {
+                if (k & half) continue;
+                u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
+                fwd_bfly(x[k], x[k + half], tw, q, qinv, red);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k++) sm[pad_idx(base + (k << LOB))] = x[k];
+    }
+}
+
+// One register round of the inverse transform (GS) on chunk-local stages [A, A+RB), processed deepest first.
+template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE>
+__device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const u64* roots, u64 q, u64 qinv, u64 ninv,
+                                          int s1, int chunk, int tid) {
+    constexpr int G = 16 >> RB;
+    constexpr int RR = 1 << RB;
+    constexpr int LOB = CL - A - RB;
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int g = tid * G + gi;
+        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
+        const int base = (hi << (CL - A)) + lo;
+        u64 x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) x[k] = sm[pad_idx(base + (k << LOB))];
+#pragma unroll
+        for (int u = RB - 1; u >= 0; u--) {
+            const int half = 1 << (RB - 1 - u);
+            const int s = s1 + A + u;
+            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+#pragma unroll
+            for (int k = 0; k < RR; k++) {
+                if (k & half) continue;
+                u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
+                inv_bfly(x[k], x[k + half], tw, q, qinv);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k++) {
+            const int idx = base + (k << LOB);
+            if (TO_GLOBAL) gdst[idx] = SCALE ? mred(x[k], ninv, q, qinv) : x[k];
+            else sm[pad_idx(idx)] = x[k];
+        }
+    }
+}
+
+template <int CL>
+__global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1)
+ntt_chunk_fwd_kernel(NttParams p) {
+    constexpr int C = 1 << CL;
+    constexpr int T = C / 16;
+    constexpr int R0 = round_bits(CL, 0), R1 = round_bits(CL, 1), R2 = round_bits(CL, 2);
+    extern __shared__ u64 sm[];
+    const int row = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
+    const LimbConst L = p.limbs[p.rm.limb[row]];
+    const int s1 = p.logN - CL;
+    // for logN > 12 the strided pass already moved the data to `out`
+    const u64* src = (s1 > 0 ? (const u64*)p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs
+                             : p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs) + ((size_t)chunk << CL);
+    u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
+    const u64 q = L.q, qinv = L.qinv;
+    fwd_round<CL, 0, R0, true>(sm, src, L.roots_fwd, q, qinv, s1, p.logN, chunk, tid);
+    __syncthreads();
+    if constexpr (R1 > 0) {
+        fwd_round<CL, R0, R1, false>(sm, nullptr, L.roots_fwd, q, qinv, s1, p.logN, chunk, tid);
+        __syncthreads();
+    }
+    if constexpr (R2 > 0) {
+        fwd_round<CL, R0 + R1, R2, false>(sm, nullptr, L.roots_fwd, q, qinv, s1, p.logN, chunk, tid);
+        __syncthreads();
+    }
+    const bool canon = (p.mode == NTT_CANONICAL);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int idx = k * T + tid;
+        u64 v = sm[pad_idx(idx)];
+        if (canon) v = bred_add(v, q, L.bred_hi);   // reducevec, ring/ntt.go:176
+        dst[idx] = v;
+    }
+}
+
+template <int CL>
+__global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1)
+ntt_chunk_inv_kernel(NttParams p) {
+    constexpr int C = 1 << CL;
+    constexpr int T = C / 16;
+    constexpr int NR = num_rounds(CL);
+    constexpr int R0 = round_bits(CL, 0), R1 = round_bits(CL, 1), R2 = round_bits(CL, 2);
+    extern __shared__ u64 sm[];
+    const int row = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
+    const LimbConst L = p.limbs[p.rm.limb[row]];
+    const int s1 = p.logN - CL;
+    const u64* src = p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs + ((size_t)chunk << CL);
+    u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
+    const u64 q = L.q, qinv = L.qinv;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int idx = k * T + tid;
+        sm[pad_idx(idx)] = src[idx];
+    }
+    __syncthreads();
+    // deepest round first
+    if constexpr (NR == 3) {
+        inv_round<CL, R0 + R1, R2, false, false>(sm, nullptr, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
+        __syncthreads();
+    }
+    if constexpr (NR >= 2) {
+        inv_round<CL, R0, R1, false, false>(sm, nullptr, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
+        __syncthreads();
+    }
+    if (s1 == 0) inv_round<CL, 0, R0, true, true>(sm, dst, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
+    else         inv_round<CL, 0, R0, true, false>(sm, dst, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------
+template <int CL>
+static int launch_chunk(bool inverse, const NttParams& p, dim3 grid, cudaStream_t st) {
+    constexpr int C = 1 << CL;
+    constexpr int T = C >= 16 ? C / 16 : 1;
+    size_t smem = (size_t)(C + (C >> 4) + 1) * sizeof(u64);
+    if (inverse) ntt_chunk_inv_kernel<CL><<<grid, T, smem, st>>>(p);
+    else         ntt_chunk_fwd_kernel<CL><<<grid, T, smem, st>>>(p);
+    LGPU_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_chunk_dyn(int cl, bool inverse, const NttParams& p, dim3 grid, cudaStream_t st) {
+    switch (cl) {
+        case 4: return launch_chunk<4>(inverse, p, grid, st);
+        case 5: return launch_chunk<5>(inverse, p, grid, st);
+        case 6: return launch_chunk<6>(inverse, p, grid, st);
+        case 7: return launch_chunk<7>(inverse, p, grid, st);
+        case 8: return launch_chunk<8>(inverse, p, grid, st);
+        case 9: return launch_chunk<9>(inverse, p, grid, st);
+        case 10: return launch_chunk<10>(inverse, p, grid, st);
+        case 11: return launch_chunk<11>(inverse, p, grid, st);
+        case 12: return launch_chunk<12>(inverse, p, grid, st);
+    }
+    set_error("unsupported chunk size");
+    return -1;
+}
+
+template <bool INV>
+static int launch_strided(int rl, const NttParams& p, int rows, int batch, cudaStream_t st) {
+    const int N = 1 << p.logN;
+    const int threads_total = N >> rl;
+    const int bs = threads_total < 256 ? threads_total : 256;
+    dim3 grid((threads_total + bs - 1) / bs, rows, batch);
+    switch (rl) {
+        case 1: ntt_strided_kernel<1, INV><<<grid, bs, 0, st>>>(p); break;
+        case 2: ntt_strided_kernel<2, INV><<<grid, bs, 0, st>>>(p); break;
+        case 3: ntt_strided_kernel<3, INV><<<grid, bs, 0, st>>>(p); break;
+        case 4: ntt_strided_kernel<4, INV><<<grid, bs, 0, st>>>(p); break;
+        case 5: ntt_strided_kernel<5, INV><<<grid, bs, 0, st>>>(p); break;
+        default: set_error("unsupported strided radix"); return -1;
+    }
+    LGPU_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int check_common(const Ctx* c, const RowMap& rm, int batch) {
+    if (c->logN < 4 || c->logN > 17) { set_error("NTT requires 16 <= N <= 2^17"); return -1; }
+    if (rm.nrows <= 0 || rm.nrows > kMaxRows || batch <= 0 || batch > 65535) { set_error("bad rows/batch"); return -1; }
+    if (c->ring_type != 0) { set_error("conjugate-invariant NTT is not implemented on device"); return -1; }
+    return 0;
+}
+
+int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
+    if (check_common(c, rm, batch)) return -1;
+    NttParams p;
+    p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
+    p.in_rs = in.row_stride; p.in_bs = in.batch_stride; p.out_rs = out.row_stride; p.out_bs = out.batch_stride;
+    p.logN = c->logN; p.mode = mode; p.ci = 0;
+    const int cl = c->logN > 12 ? 12 : c->logN;
+    const int s1 = c->logN - cl;
+    if (s1 > 0 && launch_strided<false>(s1, p, rm.nrows, batch, st)) return -1;
+    dim3 grid(1u << s1, rm.nrows, batch);
+    return launch_chunk_dyn(cl, false, p, grid, st);
+}
+
+int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
+    (void)mode;  // INTTLazy == INTT for N >= 16 (ring/ntt.go:197-206)
+    if (check_common(c, rm, batch)) return -1;
+    NttParams p;
+    p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
+    p.in_rs = in.row_stride; p.in_bs = in.batch_stride; p.out_rs = out.row_stride; p.out_bs = out.batch_stride;
+    p.logN = c->logN; p.mode = mode; p.ci = 0;
+    const int cl = c->logN > 12 ? 12 : c->logN;
+    const int s1 = c->logN - cl;
+    dim3 grid(1u << s1, rm.nrows, batch);
+    if (launch_chunk_dyn(cl, true, p, grid, st)) return -1;
+    if (s1 > 0) {
+        // second pass works in place on `out`
+        NttParams p2 = p;
+        p2.in = out.p; p2.in_rs = out.row_stride; p2.in_bs = out.batch_stride;
+        return launch_strided<true>(s1, p2, rm.nrows, batch, st);
+    }
+    return 0;
+}
+
+}  // namespace lgpu

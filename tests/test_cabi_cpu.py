@@ -1,0 +1,50 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/lattigo_b200.h declares, and its host-side table generation (device < 0: no CUDA call) matches the
+oracle's independent big-integer generation."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import helpers as H
+
+
+def test_library_exports_every_declared_symbol():
+    import lattigo_b200 as lb
+    L = lb.lib()
+    syms = lb.declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert b"sm_100a" in L.lgpu_version()
+
+
+def test_host_tables_match_oracle():
+    import lattigo_b200 as lb
+    logN, N = 11, 2048
+    Q, P = H.Qi60[:4], H.Pi60[:3]
+    ctx = lb.Context(logN, Q, P, device=-1)
+    for ring, mods in ((0, Q), (1, P)):
+        oring = O.Ring(N, mods)
+        for i, q in enumerate(mods):
+            s = oring.SubRings[i]
+            t = [int(x) for x in ctx.table(ring, i, 0)]
+            assert t == [q, s.MRedConstant, s.BRedConstant[0], s.BRedConstant[1], s.NInv, s.PrimitiveRoot]
+            assert np.array_equal(ctx.table(ring, i, 1), s.RootsForward)
+            assert np.array_equal(ctx.table(ring, i, 2), s.RootsBackward)
+            if i >= 1:
+                assert [int(x) for x in ctx.table(ring, i, 3)] == oring.RescaleConstants[i - 1]
+    ctx.close()
+
+
+def test_host_only_context_refuses_device_work_and_bad_params():
+    import lattigo_b200 as lb
+    ctx = lb.Context(8, H.Qi60[:2], device=-1)
+    with pytest.raises(lb.LgpuError):
+        ctx.sync()
+    with pytest.raises(lb.LgpuError):
+        lb.Context(3, H.Qi60[:1], device=-1)          # N < 16
+    with pytest.raises(lb.LgpuError):
+        lb.Context(8, [H.Qi60[0], H.Qi60[0]], device=-1)
+    with pytest.raises(lb.LgpuError):
+        lb.Context(8, [97], device=-1)                 # 97 != 1 mod 512
+    ctx.close()
