@@ -13,7 +13,7 @@
  *     ring.Poly{Coeffs [][]uint64} (ring/poly.go:13-15) maps onto it with Coeffs[i] = row i.
  *   - `ring` selects the moduli chain: LGPU_RING_Q or LGPU_RING_P (ringqp.Ring{RingQ,RingP},
  *     ring/ringqp/ring.go:15-17). `level` is the reference's level (number of limbs - 1).
- *   - All calls are asynchronous on `stream` (a cudaStream_t cast to void*; NULL = the context's
+ *   - All calls are asynchronous on `stream` (a cudaStream_t cast to void*; NULL = the CUDA default
  *     stream); lgpu_sync() before host access. Entry points ending in _host take HOST pointers and
  *     include the copies.
  *   - Return 0 on success, non-zero on error with lgpu_last_error() (thread-local) describing it.

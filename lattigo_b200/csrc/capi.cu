@@ -9,7 +9,9 @@ struct lgpu_ctx {
     Ctx c;
 };
 
-static inline cudaStream_t pick_stream(lgpu_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->c.stream; }
+// NULL means the CUDA default stream (same convention as the runtime API), so that callers which pass their
+// framework's current stream (0 for torch's default stream) stay ordered with their own work.
+static inline cudaStream_t pick_stream(lgpu_ctx* ctx, void* stream) { (void)ctx; return (cudaStream_t)stream; }
 
 #define REQUIRE(cond, msg)                 \
     do {                                   \
