@@ -138,6 +138,109 @@ int lgpu_vecop(lgpu_ctx* ctx, int ring, int level, int opcode, const uint64_t* p
 int lgpu_subring_vecop(lgpu_ctx* ctx, int ring, int limb, int opcode, const uint64_t* p1, const uint64_t* p2,
                        uint64_t* p3, uint64_t s0, uint64_t s1, int n, void* stream);
 
+
+/* ---- automorphisms (ring/automorphism.go) --------------------------------------------------------------- */
+/* AutomorphismNTTIndex (:12-34): writes the N-entry uint64 look-up table to DEVICE memory `index_out`. */
+int lgpu_automorphism_ntt_index(lgpu_ctx* ctx, uint64_t gal_el, uint64_t* index_out, void* stream);
+/* Ring.AutomorphismNTTWithIndex (:50-77) and ...ThenAddLazy (:82-109, accumulate != 0). Cannot be in-place. */
+int lgpu_automorphism_ntt_with_index(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, const uint64_t* index,
+                                     uint64_t* out, int accumulate, int batch, size_t batch_stride, void* stream);
+/* Ring.AutomorphismNTT (:38-45): index computed on the fly. */
+int lgpu_automorphism_ntt(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t gal_el, uint64_t* out,
+                          int batch, size_t batch_stride, void* stream);
+/* Ring.Automorphism (:113-176), coefficient domain, Standard ring. Cannot be in-place. */
+int lgpu_automorphism(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t gal_el, uint64_t* out,
+                      int batch, size_t batch_stride, void* stream);
+
+/* ---- RNS basis extension (ring/basis_extension.go) -------------------------------------------------------
+ * polQ has levelQ+1 rows, polP has levelP+1 rows; `batch` polynomials with the given strides (words). */
+/* BasisExtender.ModUpQtoP (:177-190) / ModUpPtoQ (:195-209): outputs are the reference's exact (non-canonical,
+ * < 2p) representatives. */
+int lgpu_modup_qtop(lgpu_ctx* ctx, int level_q, int level_p, const uint64_t* pol_q, uint64_t* pol_p,
+                    int batch, size_t stride_q, size_t stride_p, void* stream);
+int lgpu_modup_ptoq(lgpu_ctx* ctx, int level_p, int level_q, const uint64_t* pol_p, uint64_t* pol_q,
+                    int batch, size_t stride_p, size_t stride_q, void* stream);
+/* BasisExtender.ModDownQPtoQ (:215-228), ModDownQPtoQNTT (:235-256), ModDownQPtoP (:262-278) */
+int lgpu_moddown_qp_to_q(lgpu_ctx* ctx, int level_q, int level_p, const uint64_t* p1q, const uint64_t* p1p, uint64_t* p2q,
+                         int batch, size_t stride_q, size_t stride_p, void* stream);
+int lgpu_moddown_qp_to_q_ntt(lgpu_ctx* ctx, int level_q, int level_p, const uint64_t* p1q, const uint64_t* p1p, uint64_t* p2q,
+                             int batch, size_t stride_q, size_t stride_p, void* stream);
+int lgpu_moddown_qp_to_p(lgpu_ctx* ctx, int level_q, int level_p, const uint64_t* p1q, const uint64_t* p1p, uint64_t* p2p,
+                         int batch, size_t stride_q, size_t stride_p, void* stream);
+/* Decomposer.DecomposeAndSplit (:381-502). p0q: coefficient domain. In the reconstruction branch the rows of
+ * p1q that belong to the digit itself are left untouched (the reference leaves unspecified values there and its
+ * only caller, DecomposeSingleNTT, overwrites them). */
+int lgpu_decompose_and_split(lgpu_ctx* ctx, int level_q, int level_p, int nb_pi, int digit, const uint64_t* p0q,
+                             uint64_t* p1q, uint64_t* p1p, int batch, size_t stride_q, size_t stride_p, void* stream);
+
+/* ---- rescaling (ring/scaling.go) ---------------------------------------------------------------------------
+ * Ring.DivRoundByLastModulus[NTT] (:101-144), DivFloorByLastModulus[NTT] (:6-33) and the *Many forms
+ * (:37-97, :148-212). `level` = input level; the output has level - nb_rescales + 1 rows. flags: bit0 = round
+ * (else floor), bit1 = NTT domain. In-place allowed. Strides in words. */
+#define LGPU_DIV_ROUND 1
+#define LGPU_DIV_NTT 2
+int lgpu_div_by_last_modulus_many(lgpu_ctx* ctx, int ring, int level, int flags, int nb_rescales, const uint64_t* p0,
+                                  uint64_t* p1, int batch, size_t stride_in, size_t stride_out, void* stream);
+
+/* ---- rlwe.Evaluator key-switch family (core/rlwe/evaluator_gadget_product.go) --------------------------------
+ * Evaluation keys are uploaded once as a device array in the layout of rlwe.GadgetCiphertext.Value
+ * (core/rlwe/gadgetciphertext.go:19-45): data[digit][pw2][component][limb][coeff] with the (level_q+1) Q limbs
+ * first, then the (level_p+1) P limbs; always NTT + Montgomery form (core/rlwe/keygenerator.go:309-318). */
+typedef struct {
+    const uint64_t* data;         /* device pointer */
+    int level_q, level_p;         /* levels of the key (level_p = -1: no P) */
+    int base_two_decomposition;   /* GadgetCiphertext.BaseTwoDecomposition */
+    int n_digits;                 /* len(Value) */
+    int n_pw2_max;                /* max_i len(Value[i]) (second array dimension) */
+    const int* pw2_sizes;         /* HOST array, len(Value[i]) per digit; NULL = all 1 */
+} lgpu_gadget_ct;
+
+/* Evaluator.GadgetProduct (:16-36): ct = ModDown(<decomp(cx), evk>), cx and ct in the NTT domain.
+ * cx: level_q+1 rows; ct0/ct1: level_q+1 rows each. batch with strides in words. */
+int lgpu_gadget_product(lgpu_ctx* ctx, int level_q, const uint64_t* cx, const lgpu_gadget_ct* evk,
+                        uint64_t* ct0, uint64_t* ct1, int batch, size_t stride_cx, size_t stride_ct, void* stream);
+/* Evaluator.GadgetProductLazy (:108-127): result mod QP, not divided by P. acc{0,1}q: level_q+1 rows,
+ * acc{0,1}p: level_p+1 rows (canonical residues, as the reference's trailing Reduce leaves them). */
+int lgpu_gadget_product_lazy(lgpu_ctx* ctx, int level_q, const uint64_t* cx, const lgpu_gadget_ct* evk,
+                             uint64_t* acc0q, uint64_t* acc0p, uint64_t* acc1q, uint64_t* acc1p,
+                             int batch, size_t stride_cx, size_t stride_q, size_t stride_p, void* stream);
+/* Evaluator.ModDown (:39-97), NTT -> NTT case: ct[k] = ModDownQPtoQNTT(acc[k]). */
+int lgpu_evaluator_moddown(lgpu_ctx* ctx, int level_q, int level_p, const uint64_t* acc0q, const uint64_t* acc0p,
+                           const uint64_t* acc1q, const uint64_t* acc1p, uint64_t* ct0, uint64_t* ct1,
+                           int batch, size_t stride_q, size_t stride_p, size_t stride_ct, void* stream);
+/* Evaluator.DecomposeSingleNTT (:487-510). c2ntt / c2inv: the input in and out of the NTT domain. */
+int lgpu_decompose_single_ntt(lgpu_ctx* ctx, int level_q, int level_p, int nb_pi, int digit, const uint64_t* c2ntt,
+                              const uint64_t* c2inv, uint64_t* c2q, uint64_t* c2p, int batch, size_t stride_in,
+                              size_t stride_q, size_t stride_p, void* stream);
+/* Evaluator.DecomposeNTT (:459-483). decomp: device array [digit][batch][level_q+1 + level_p+1][N]
+ * (BuffDecompQP[digit].Q rows then .P rows). */
+int lgpu_decompose_ntt(lgpu_ctx* ctx, int level_q, int level_p, int nb_pi, const uint64_t* c2, int c2_is_ntt,
+                       uint64_t* decomp, int batch, size_t stride_in, void* stream);
+/* Evaluator.GadgetProductHoisted (:348-368) / GadgetProductHoistedLazy (:381-399) on a DecomposeNTT result. */
+int lgpu_gadget_product_hoisted(lgpu_ctx* ctx, int level_q, const uint64_t* decomp, const lgpu_gadget_ct* evk,
+                                uint64_t* ct0, uint64_t* ct1, int batch, size_t stride_ct, void* stream);
+int lgpu_gadget_product_hoisted_lazy(lgpu_ctx* ctx, int level_q, const uint64_t* decomp, const lgpu_gadget_ct* evk,
+                                     uint64_t* acc0q, uint64_t* acc0p, uint64_t* acc1q, uint64_t* acc1p,
+                                     int batch, size_t stride_q, size_t stride_p, void* stream);
+/* Evaluator.Automorphism (core/rlwe/evaluator_automorphism.go:13-57) and AutomorphismHoisted (:63-102,
+ * decomp != NULL), degree-1 NTT-domain ciphertexts stored as [batch][2][level+1][N]. */
+int lgpu_evaluator_automorphism(lgpu_ctx* ctx, int level, const uint64_t* ct_in, uint64_t gal_el,
+                                const lgpu_gadget_ct* gk, const uint64_t* decomp, uint64_t* ct_out, int batch, void* stream);
+/* Evaluator.Relinearize (core/rlwe/evaluator_evaluationkey.go:121-148): ct_in [batch][3][level+1][N] ->
+ * ct_out [batch][2][level+1][N]. */
+int lgpu_evaluator_relinearize(lgpu_ctx* ctx, int level, const uint64_t* ct_in, const lgpu_gadget_ct* rlk,
+                               uint64_t* ct_out, int batch, void* stream);
+
+/* ---- fused batch entry points for the measured op sequences ---------------------------------------------------
+ * ckks.Evaluator.MulRelinNew(ct_a, ct_b) followed by Rescale (schemes/ckks/evaluator.go:719-872, :477-515;
+ * nb_rescales = Parameters.LevelsConsumedPerRescaling(), 0 = no rescale). ct_a, ct_b: [batch][2][level+1][N]
+ * (NTT domain); ct_out: [batch][2][level+1-nb_rescales][N]. _host: pinned or pageable HOST buffers, copies
+ * included and pipelined in chunks of `chunk` ciphertext pairs (0 = default). */
+int lgpu_ckks_mulrelin_rescale_batch(lgpu_ctx* ctx, int level, const uint64_t* ct_a, const uint64_t* ct_b,
+                                     const lgpu_gadget_ct* rlk, int nb_rescales, uint64_t* ct_out, int batch, void* stream);
+int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64_t* ct_a_host, const uint64_t* ct_b_host,
+                                          const lgpu_gadget_ct* rlk, int nb_rescales, uint64_t* ct_out_host, int batch, int chunk);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,28 @@ def lib():
             "lgpu_subring_intt": [vp, i, i, vp, vp, i, vp],
             "lgpu_vecop": [vp, i, i, i, vp, vp, vp, vp, vp, i, z, vp],
             "lgpu_subring_vecop": [vp, i, i, i, vp, vp, vp, u64, u64, i, vp],
+            "lgpu_automorphism_ntt_index": [vp, u64, vp, vp],
+            "lgpu_automorphism_ntt_with_index": [vp, i, i, vp, vp, vp, i, i, z, vp],
+            "lgpu_automorphism_ntt": [vp, i, i, vp, u64, vp, i, z, vp],
+            "lgpu_automorphism": [vp, i, i, vp, u64, vp, i, z, vp],
+            "lgpu_modup_qtop": [vp, i, i, vp, vp, i, z, z, vp],
+            "lgpu_modup_ptoq": [vp, i, i, vp, vp, i, z, z, vp],
+            "lgpu_moddown_qp_to_q": [vp, i, i, vp, vp, vp, i, z, z, vp],
+            "lgpu_moddown_qp_to_q_ntt": [vp, i, i, vp, vp, vp, i, z, z, vp],
+            "lgpu_moddown_qp_to_p": [vp, i, i, vp, vp, vp, i, z, z, vp],
+            "lgpu_decompose_and_split": [vp, i, i, i, i, vp, vp, vp, i, z, z, vp],
+            "lgpu_div_by_last_modulus_many": [vp, i, i, i, i, vp, vp, i, z, z, vp],
+            "lgpu_gadget_product": [vp, i, vp, vp, vp, vp, i, z, z, vp],
+            "lgpu_gadget_product_lazy": [vp, i, vp, vp, vp, vp, vp, vp, i, z, z, z, vp],
+            "lgpu_evaluator_moddown": [vp, i, i, vp, vp, vp, vp, vp, vp, i, z, z, z, vp],
+            "lgpu_decompose_single_ntt": [vp, i, i, i, i, vp, vp, vp, vp, i, z, z, z, vp],
+            "lgpu_decompose_ntt": [vp, i, i, i, vp, i, vp, i, z, vp],
+            "lgpu_gadget_product_hoisted": [vp, i, vp, vp, vp, vp, i, z, vp],
+            "lgpu_gadget_product_hoisted_lazy": [vp, i, vp, vp, vp, vp, vp, vp, i, z, z, vp],
+            "lgpu_evaluator_automorphism": [vp, i, vp, u64, vp, vp, vp, i, vp],
+            "lgpu_evaluator_relinearize": [vp, i, vp, vp, vp, i, vp],
+            "lgpu_ckks_mulrelin_rescale_batch": [vp, i, vp, vp, vp, i, vp, i, vp],
+            "lgpu_ckks_mulrelin_rescale_batch_host": [vp, i, vp, vp, vp, i, vp, i, i],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -60,6 +82,13 @@ def lib():
         L.lgpu_destroy.restype = None
         _lib = L
     return _lib
+
+
+class GadgetCtStruct(ctypes.Structure):
+    """lgpu_gadget_ct (include/lattigo_b200.h)."""
+    _fields_ = [("data", ctypes.c_void_p), ("level_q", ctypes.c_int), ("level_p", ctypes.c_int),
+                ("base_two_decomposition", ctypes.c_int), ("n_digits", ctypes.c_int), ("n_pw2_max", ctypes.c_int),
+                ("pw2_sizes", ctypes.POINTER(ctypes.c_int))]
 
 
 def check(rc):

@@ -31,7 +31,7 @@ int make_rowmap(const Ctx& c, int ring, int level, RowMap& rm) {
     if (level >= n) { set_error("level cannot be larger than max level"); return -1; }
     rm.nrows = level + 1;
     const int off = ring == LGPU_RING_Q ? 0 : c.nQ;
-    for (int i = 0; i <= level; i++) rm.limb[i] = (unsigned char)(off + i);
+    for (int i = 0; i <= level; i++) { rm.limb[i] = (unsigned char)(off + i); rm.drow[i] = (unsigned char)i; }
     return 0;
 }
 int make_rowmap_single(const Ctx& c, int ring, int limb, RowMap& rm) {
@@ -40,6 +40,7 @@ int make_rowmap_single(const Ctx& c, int ring, int limb, RowMap& rm) {
     if (limb < 0 || limb >= n) { set_error("limb index out of range"); return -1; }
     rm.nrows = 1;
     rm.limb[0] = (unsigned char)((ring == LGPU_RING_Q ? 0 : c.nQ) + limb);
+    rm.drow[0] = 0;
     return 0;
 }
 }  // namespace lgpu

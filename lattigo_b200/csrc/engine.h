@@ -34,7 +34,8 @@ struct LimbConst {
 // Which global limb each row of a launch uses.
 struct RowMap {
     int nrows;
-    unsigned char limb[kMaxRows];
+    unsigned char limb[kMaxRows];  // global limb index of launch row r
+    unsigned char drow[kMaxRows];  // data row (within the polynomial) of launch row r
 };
 
 struct HostSubRing {
@@ -124,6 +125,15 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
 int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st);
 
 int launch_vecop(const Ctx* c, const RowMap& rm, int op, CSpan p1, CSpan p2, Span p3, int batch,
-                 const u64* d_s0, const u64* d_s1, u64 s0, u64 s1, int n, cudaStream_t st);
+                 const u64* h_s0, const u64* h_s1, u64 s0, u64 s1, int n, cudaStream_t st);
+
+// basisext.cu
+int launch_modup_qp(const Ctx* c, bool toP, int levelQ, int levelP, CSpan in, Span out, int batch, cudaStream_t st);
+int launch_decompose_and_split(const Ctx* c, int levelQ, int levelP, int nbPi, int digit, CSpan p0Q, Span p1Q, Span p1P,
+                               int batch, cudaStream_t st);
+
+// capi.cu helpers
+int make_rowmap(const Ctx& c, int ring, int level, RowMap& rm);
+int make_rowmap_single(const Ctx& c, int ring, int limb, RowMap& rm);
 
 }  // namespace lgpu

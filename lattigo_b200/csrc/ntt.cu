@@ -58,8 +58,9 @@ __device__ __forceinline__ void inv_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qin
 template <int RL, bool INVERSE>
 __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
     constexpr int R = 1 << RL;
-    const int row = blockIdx.y, b = blockIdx.z;
-    const LimbConst L = p.limbs[p.rm.limb[row]];
+    const int b = blockIdx.z;
+    const LimbConst L = p.limbs[p.rm.limb[blockIdx.y]];
+    const int row = p.rm.drow[blockIdx.y];
     const int N = 1 << p.logN;
     const int stride = N >> RL;
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,8 +203,9 @@ ntt_chunk_fwd_kernel(NttParams p) {
     constexpr int T = C / 16;
     constexpr int R0 = round_bits(CL, 0), R1 = round_bits(CL, 1), R2 = round_bits(CL, 2);
     extern __shared__ u64 sm[];
-    const int row = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
-    const LimbConst L = p.limbs[p.rm.limb[row]];
+    const int b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
+    const LimbConst L = p.limbs[p.rm.limb[blockIdx.y]];
+    const int row = p.rm.drow[blockIdx.y];
     const int s1 = p.logN - CL;
     // for logN > 12 the strided pass already moved the data to `out`
     const u64* src = (s1 > 0 ? (const u64*)p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs
@@ -238,8 +240,9 @@ ntt_chunk_inv_kernel(NttParams p) {
     constexpr int NR = num_rounds(CL);
     constexpr int R0 = round_bits(CL, 0), R1 = round_bits(CL, 1), R2 = round_bits(CL, 2);
     extern __shared__ u64 sm[];
-    const int row = blockIdx.y, b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
-    const LimbConst L = p.limbs[p.rm.limb[row]];
+    const int b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
+    const LimbConst L = p.limbs[p.rm.limb[blockIdx.y]];
+    const int row = p.rm.drow[blockIdx.y];
     const int s1 = p.logN - CL;
     const u64* src = p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs + ((size_t)chunk << CL);
     u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
