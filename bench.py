@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- contract benchmark of the B200-native RNS ring engine.
+
+Metric (BASELINE.json): CKKS ciphertext x ciphertext MulRelin (+ Rescale) per second at N = 2^16, L = 44
+(44 Q-limbs + 4 P-limbs: the synthetic literal LogQ = [56] + [45]*43, LogP = [55]*4 of SURVEY 8), plus the
+NTT's achieved HBM roofline fraction.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the CPU arm: the oracle ("port" of the reference's
+                                                           pure-Go path; Go is not installed) on all host cores
+
+A "step" = one pass of MulRelinNew + Rescale over a batch of `--batch` synthetic ciphertext pairs per GPU
+(uniform residues, random evaluation key: SURVEY 8(d)). `value` times the device-resident path (inputs already
+in HBM; the batch is > L2 so no flush is needed), `e2e` the same op through the C ABI's host-buffer entry point
+with H2D / D2H inside the timed region. Ciphertexts shard one batch per GPU, evaluation key broadcast once over
+NCCL at setup, no collective on the hot path (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CKKS ct x ct mul+relin(+rescale)/s at N=2^16 L=44"
+UNIT = "ct/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preset", default="CKKS_L44")
+    ap.add_argument("--batch", type=int, default=64, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="(reference arm) pairs per step; 0 = one per core")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle, one ciphertext pair per worker process (the reference's own parallelism is "one goroutine
+# per ciphertext", schemes/ckks/ckks_benchmarks_test.go:218-229)
+# ----------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_setup(preset_name):
+    import numpy as np
+    from lattigo_b200 import params as presets
+    from oracle import oracle as O
+    s = presets.PRESETS[preset_name]
+    params = O.Parameters(s["logN"], s["Q"], s["P"])
+    N = params.N()
+    rng = np.random.default_rng(1234)
+    level, levelP = len(s["Q"]) - 1, len(s["P"]) - 1
+    nd = params.BaseRNSDecompositionVectorSize(level, levelP)
+    mods = s["Q"] + s["P"]
+
+    def rand_rows(ms, lead):
+        out = np.empty(tuple(lead) + (len(ms), N), dtype=np.uint64)
+        for i, m in enumerate(ms):
+            out[..., i, :] = rng.integers(0, m, tuple(lead) + (N,), dtype=np.uint64)
+        return out
+
+    evk = O.GadgetCiphertext(rand_rows(mods, (nd, 1, 2)), level + 1, levelP + 1)
+    a = rand_rows(s["Q"], (2,))
+    b = rand_rows(s["Q"], (2,))
+    _CPU.update(ev=O.CKKSEvaluator(params, evk), a=a, b=b)
+
+
+def _cpu_one_pair(_):
+    ev, a, b = _CPU["ev"], _CPU["a"], _CPU["b"]
+    t = time.perf_counter()
+    m = ev.MulRelinNew([a[0], a[1]], [b[0], b[1]])
+    ev.Rescale(m)
+    return time.perf_counter() - t
+
+
+def run_cpu_arm(args, steps, warmup, pairs_per_step=0):
+    """Times `steps` steps of `pairs_per_step` ciphertext pairs on all host cores (fork pool, no CUDA in this process)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    pairs = pairs_per_step or cores
+    _cpu_setup(args.preset)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=min(cores, pairs)) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_one_pair, range(pairs), chunksize=1)
+        t0 = time.perf_counter()
+        per_pair = []
+        for _ in range(steps):
+            per_pair += pool.map(_cpu_one_pair, range(pairs), chunksize=1)
+        dt = time.perf_counter() - t0
+    return {"value": pairs * steps / dt, "cores": min(cores, pairs), "pairs_per_step": pairs, "steps": steps,
+            "seconds": dt, "single_pair_seconds_median": sorted(per_pair)[len(per_pair) // 2]}
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if os.environ.get("LGPU_BENCH_MALLOC") != "1":
+        # The reference recycles its scratch polynomials through sync.Pool (ring/pool.go); numpy would instead
+        # mmap/munmap (and page-fault) every 23 MB temporary. Keep freed blocks in the heap so the CPU arm is not
+        # handicapped by the allocator: glibc tunables must be set before the interpreter starts -> re-exec once.
+        env = dict(os.environ, LGPU_BENCH_MALLOC="1", MALLOC_MMAP_THRESHOLD_="33554432", MALLOC_TRIM_THRESHOLD_="68719476736",
+                   MALLOC_TOP_PAD_="268435456", MALLOC_ARENA_MAX="1")
+        os.execve(sys.executable, [sys.executable] + sys.argv, env)
+    r = run_cpu_arm(args, args.steps, args.warmup, args.cpu_sample_pairs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "ckks_mulrelin_rescale", "preset": args.preset, "pairs_per_step": r["pairs_per_step"],
+                   "note": "oracle = C/Python restatement of the reference's pure-Go path (Go toolchain absent); one pair per worker process"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": "%d steps x %d ciphertext pairs, one per core" % (args.steps, r["pairs_per_step"])},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()          # exact PID, never by pattern
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def gpu_main(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import lattigo_b200 as lb
+    from lattigo_b200 import params as presets, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    s = presets.PRESETS[args.preset]
+    logN, Q, P = s["logN"], s["Q"], s["P"]
+    N = 1 << logN
+    level, levelP = len(Q) - 1, len(P) - 1
+    nd = (level + levelP + 1) // (levelP + 1)
+    ctx = lb.Context(logN, Q, P, device=local)
+    g = torch.Generator(device=dev); g.manual_seed(1000 + rank)
+
+    def rand_rows(mods, lead):
+        out = torch.empty(tuple(lead) + (len(mods), N), dtype=torch.int64, device=dev)
+        for i, m in enumerate(mods):
+            out[..., i, :] = torch.randint(0, m, tuple(lead) + (N,), generator=g, device=dev, dtype=torch.int64)
+        return out
+
+    # evaluation key: generated on rank 0, broadcast once over NCCL; never touched again on the hot path
+    evk_t = rand_rows(Q + P, (nd, 1, 2)) if rank == 0 else torch.empty((nd, 1, 2, len(Q) + len(P), N), dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(evk_t, src=0)
+    rlk = lb.GadgetCiphertext(ctx, evk_t, level, levelP)
+    ev = lb.CKKSEvaluator(ctx, rlk)
+    B = args.batch
+    a = rand_rows(Q, (B, 2)); b = rand_rows(Q, (B, 2))
+    out = None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return ev.MulRelinRescaleNew(a, b)
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib().lgpu_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    launches = _lib.lib().lgpu_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    tt = torch.tensor([t_dev], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    value = B * world * args.steps / t_max
+
+    # ---- roofline of the dominant kernel class (NTT): same K steps with the event profiler on --------------------
+    roof = None
+    if rank == 0:
+        import ctypes
+        L = _lib.lib()
+        nk = 8
+        ms = (ctypes.c_double * nk)(); by = (ctypes.c_double * nk)()
+        sc = (ctypes.c_ulonglong * nk)(); kn = (ctypes.c_ulonglong * nk)()
+        L.lgpu_profile_enable(1)
+        for _ in range(args.steps):
+            out = step()
+        torch.cuda.synchronize()
+        L.lgpu_profile_enable(0)
+        L.lgpu_profile_read(ms, by, sc, kn)
+        names = ["ntt_fwd", "ntt_inv", "vecop", "modup", "mac", "tensor", "automorphism", "fused"]
+        classes = {names[i]: {"ms": ms[i], "alg_GB": by[i] / 1e9, "scopes": int(sc[i]), "kernels": int(kn[i]),
+                              "alg_GBs": (by[i] / 1e9) / (ms[i] * 1e-3) if ms[i] > 0 else None} for i in range(nk) if sc[i]}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ntt_ms = ms[0] + ms[1]; ntt_b = by[0] + by[1]
+        ach = (ntt_b / 1e9) / (ntt_ms * 1e-3) if ntt_ms > 0 else 0.0
+        tot = sum(ms[i] for i in range(nk)) or 1.0
+        roof = {"bound": "hbm", "kernel": "ntt (forward + inverse transforms: strided pass + chunk pass kernels)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": None, "alg_bytes_per_limb_transform": 16 * N, "share_of_step": ntt_ms / tot,
+                "avg_us_per_limb_transform": 1e3 * ntt_ms / max(1.0, ntt_b / (16.0 * N)), "classes": classes}
+    barrier()
+
+    # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region) ------
+    e2e = None
+    if not args.no_e2e:
+        nq = level + 1
+        ha = torch.empty((B, 2, nq, N), dtype=torch.int64).pin_memory()
+        hb = torch.empty((B, 2, nq, N), dtype=torch.int64).pin_memory()
+        ho = torch.empty((B, 2, nq - 1, N), dtype=torch.int64).pin_memory()
+        ha.copy_(a); hb.copy_(b)
+        torch.cuda.synchronize()
+        na, nb_, no = ha.numpy().view(np.uint64), hb.numpy().view(np.uint64), ho.numpy().view(np.uint64)
+        ev.MulRelinRescaleHost(na, nb_, no, chunk=8)     # warm-up (allocators, page touching)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            ev.MulRelinRescaleHost(na, nb_, no, chunk=8)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        td = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        e2e_ok = bool(torch.equal(ho.to(dev), out)) if out is not None else None
+        e2e = {"value": B * world * e2e_steps / float(td.item()), "unit": UNIT, "h2d_bytes_per_step": int(2 * ha.numel() * 8),
+               "d2h_bytes_per_step": int(ho.numel() * 8), "steps": e2e_steps, "matches_device_path": e2e_ok,
+               "entry_point": "lgpu_ckks_mulrelin_rescale_batch_host (pinned host buffers, 2-stream chunked pipeline)"}
+        del ha, hb, ho
+    barrier()
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            # bounded CPU sample in a separate process (fork pool there; this process holds a CUDA context)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                    "--preset", args.preset], capture_output=True, text=True, timeout=900)
+                ref = json.loads(r.stdout.strip().splitlines()[-1])
+                cpu = ref["cpu_baseline"]
+                cpu["sample"] = "1 step x %d ciphertext pairs (one per core), oracle port" % ref["config"]["pairs_per_step"]
+            except Exception as ex:  # noqa: BLE001
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "ckks_mulrelin_rescale", "preset": args.preset, "logN": logN, "q_limbs": len(Q), "p_limbs": len(P),
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (one batch per GPU, evk broadcast once)" % world,
+                       "l2_policy": "inputs (%.1f GB per GPU) exceed L2; no flush" % (2 * a.numel() * 8 / 1e9),
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_main(args)
+    return gpu_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

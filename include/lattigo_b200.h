@@ -241,6 +241,26 @@ int lgpu_ckks_mulrelin_rescale_batch(lgpu_ctx* ctx, int level, const uint64_t* c
 int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64_t* ct_a_host, const uint64_t* ct_b_host,
                                           const lgpu_gadget_ct* rlk, int nb_rescales, uint64_t* ct_out_host, int batch, int chunk);
 
+
+/* ---- launch accounting / profiling (used by bench.py) ------------------------------------------------------- */
+enum lgpu_kclass {
+    LGPU_KCLASS_NTT_FWD = 0,   /* one forward transform of rows x batch polynomials (1 or 2 kernels) */
+    LGPU_KCLASS_NTT_INV,
+    LGPU_KCLASS_VECOP,
+    LGPU_KCLASS_MODUP,         /* basis extension / decomposition */
+    LGPU_KCLASS_MAC,           /* key-switch multiply-accumulate */
+    LGPU_KCLASS_TENSOR,
+    LGPU_KCLASS_AUTOMORPHISM,
+    LGPU_KCLASS_FUSED,
+    LGPU_KCLASS_COUNT
+};
+/* total number of CUDA kernels this library has launched in the process */
+unsigned long long lgpu_launch_count(void);
+/* When enabled every launch scope is bracketed by CUDA events on its stream. lgpu_profile_read sums (and clears)
+ * per class: elapsed ms, algorithmic bytes (compulsory read + write of the operands), scopes and kernels. */
+int lgpu_profile_enable(int on);
+int lgpu_profile_read(double* ms, double* alg_bytes, unsigned long long* scopes, unsigned long long* kernels);
+
 #ifdef __cplusplus
 }
 #endif

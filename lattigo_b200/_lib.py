@@ -73,6 +73,8 @@ def lib():
             "lgpu_evaluator_relinearize": [vp, i, vp, vp, vp, i, vp],
             "lgpu_ckks_mulrelin_rescale_batch": [vp, i, vp, vp, vp, i, vp, i, vp],
             "lgpu_ckks_mulrelin_rescale_batch_host": [vp, i, vp, vp, vp, i, vp, i, i],
+            "lgpu_profile_enable": [i],
+            "lgpu_profile_read": [vp, vp, vp, vp],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -80,6 +82,8 @@ def lib():
             if name != "lgpu_destroy":
                 f.restype = i
         L.lgpu_destroy.restype = None
+        L.lgpu_launch_count.restype = c.c_ulonglong
+        L.lgpu_launch_count.argtypes = []
         _lib = L
     return _lib
 

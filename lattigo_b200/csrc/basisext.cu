@@ -11,6 +11,7 @@
 //                                 + t_j + vtimesqmodp[j][v]  + t_j - (half mod t_j), t_j )
 // which reproduces the reference's specific (non-canonical) representative bit for bit.
 // Layout: thread = coefficient (coalesced row reads/writes), blockIdx.y = group of targets, blockIdx.z = batch.
+#include "../../include/lattigo_b200.h"
 #include "engine.h"
 #include "modarith.cuh"
 
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) decomp_single_kernel(DecompSingleParams p
 
 static int launch_modup(const ModUpParams& p, int batch, cudaStream_t st) {
     const int nT = p.nA + p.nB;
+    ProfScope ps(LGPU_KCLASS_MODUP, st, 8.0 * p.n * batch * (p.nS + nT - (p.exhi - p.exlo)), 1);
     dim3 grid((p.n + 127) / 128, (nT + p.tg - 1) / p.tg, batch);
     if (p.nS <= 4)       modup_kernel<4><<<grid, 128, 0, st>>>(p);
     else if (p.nS <= 8)  modup_kernel<8><<<grid, 128, 0, st>>>(p);
@@ -187,6 +189,7 @@ int launch_decompose_and_split(const Ctx* c, int levelQ, int levelP, int nbPi, i
         p.outA = p1Q.p; p.outA_rs = p1Q.row_stride; p.outA_bs = p1Q.batch_stride; p.nA = levelQ + 1; p.limbA0 = 0;
         p.outB = p1P.p; p.outB_rs = p1P.row_stride; p.outB_bs = p1P.batch_stride; p.nB = levelP + 1; p.limbB0 = c->nQ;
         const int nT = p.nA + p.nB;
+        ProfScope ps(LGPU_KCLASS_MODUP, st, 8.0 * p.n * batch * (1 + nT), 1);
         dim3 grid((p.n + 255) / 256, nT < 8 ? nT : 8, batch);
         decomp_single_kernel<<<grid, 256, 0, st>>>(p);
         LGPU_CUDA_OK(cudaGetLastError());

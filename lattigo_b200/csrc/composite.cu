@@ -10,6 +10,7 @@
 // All take a batch of independent polynomials / ciphertexts. Scratch comes from the stream-ordered allocator
 // (cudaMallocAsync), so concurrent callers on different streams never share buffers (the reference's ops are
 // safe for concurrent use, ring/ring.go:184-186).
+#include <cstdlib>
 #include <cstring>
 #include "../../include/lattigo_b200.h"
 #include "composite.h"
@@ -214,6 +215,7 @@ __global__ void auto_index_kernel(u64* index, int N, u64 nthroot, u64 galEl, int
 int automorphism_ntt_index(const Ctx* c, u64 galEl, u64* d_index, cudaStream_t st) {
     int lg = 0;
     while ((1ull << (lg + 1)) < c->nthroot) lg++;   // bits.Len64(NthRoot-1) - 1
+    count_launch(1);
     auto_index_kernel<<<(c->N + 255) / 256, 256, 0, st>>>(d_index, c->N, c->nthroot, galEl, lg);
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(256) auto_ntt_kernel(AutoParams p) {
 }
 int automorphism_ntt_with_index(const Ctx* c, int rows, CSpan in, const u64* d_index, Span out, bool accumulate, int batch, cudaStream_t st) {
     if (in.p == out.p) { set_error("AutomorphismNTT cannot be in-place"); return -1; }
+    ProfScope ps(LGPU_KCLASS_AUTOMORPHISM, st, 8.0 * c->N * rows * batch * (accumulate ? 3 : 2), 1);
     AutoParams p{in.p, in.row_stride, in.batch_stride, out.p, out.row_stride, out.batch_stride, d_index, c->N, accumulate ? 1 : 0};
     dim3 grid((c->N + 255) / 256, rows, batch);
     auto_ntt_kernel<<<grid, 256, 0, st>>>(p);
@@ -269,6 +272,7 @@ int automorphism_coeff(const Ctx* c, const RowMap& rm, CSpan in, u64 gen, Span o
     AutoCoeffParams p;
     p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.in_rs = in.row_stride; p.in_bs = in.batch_stride;
     p.out = out.p; p.out_rs = out.row_stride; p.out_bs = out.batch_stride; p.gen = gen; p.n = c->N; p.logN = c->logN;
+    ProfScope ps(LGPU_KCLASS_AUTOMORPHISM, st, 16.0 * c->N * rm.nrows * batch, 1);
     dim3 grid((c->N + 255) / 256, rm.nrows, batch);
     auto_coeff_kernel<<<grid, 256, 0, st>>>(p);
     LGPU_CUDA_OK(cudaGetLastError());
@@ -329,6 +333,8 @@ __global__ void __launch_bounds__(256) mac_kernel(MacParams p) {
     }
 }
 static int launch_mac(const MacParams& p, cudaStream_t st) {
+    // algorithmic bytes: evk (2 rows) once + per ciphertext x (1 row) + accumulators (2 rows written, 2 read unless first)
+    ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * p.n * (p.nq + p.np) * (2.0 + p.batch * (p.first ? 3.0 : 5.0)), 1);
     int zb = p.batch < 4 ? p.batch : 4;
     dim3 grid((p.n / 2 + 255) / 256, p.nq + p.np, zb);
     mac_kernel<<<grid, 256, 0, st>>>(p);
@@ -620,8 +626,37 @@ __global__ void __launch_bounds__(256) ckks_tensor_kernel(TensorParams p) {
 
 // ckks.Evaluator.MulRelinNew(ct0, ct1) [+ Rescale]: schemes/ckks/evaluator.go:719-872 and :477-515.
 // ctA, ctB: [batch][2][level+1][N]; out: [batch][2][level+1-nbRescales][N].
+static int ckks_mulrelin_rescale_chunk(const Ctx* c, int level, const u64* ctA, const u64* ctB, const GadgetCt& rlk, int nb_rescales,
+                                       u64* out, int batch, cudaStream_t st);
+
+// Sub-batches keep the per-ciphertext intermediates (a few hundred MB per ciphertext at N = 2^16) flowing through
+// the 126 MB L2 instead of HBM between the passes of one transform; the evaluation key is re-streamed once per
+// sub-batch. LGPU_BATCH_CHUNK overrides the default.
+static int batch_chunk() {
+    static int v = [] {
+        const char* e = getenv("LGPU_BATCH_CHUNK");
+        int x = e ? atoi(e) : 8;
+        return x > 0 ? x : 8;
+    }();
+    return v;
+}
+
 int ckks_mulrelin_rescale(const Ctx* c, int level, const u64* ctA, const u64* ctB, const GadgetCt& rlk, int nb_rescales,
                           u64* out, int batch, cudaStream_t st) {
+    if (level < 0 || level >= c->nQ) { set_error("level out of range"); return -1; }
+    if (nb_rescales < 0 || nb_rescales > level) { set_error("cannot Rescale: input Ciphertext level is too low"); return -1; }
+    const size_t N = c->N, nq = level + 1, nqo = nq - nb_rescales;
+    const int ch = batch_chunk();
+    for (int k = 0; k < batch; k += ch) {
+        const int nb = batch - k < ch ? batch - k : ch;
+        if (ckks_mulrelin_rescale_chunk(c, level, ctA + (size_t)k * 2 * nq * N, ctB + (size_t)k * 2 * nq * N, rlk, nb_rescales,
+                                        out + (size_t)k * 2 * nqo * N, nb, st)) return -1;
+    }
+    return 0;
+}
+
+static int ckks_mulrelin_rescale_chunk(const Ctx* c, int level, const u64* ctA, const u64* ctB, const GadgetCt& rlk, int nb_rescales,
+                                       u64* out, int batch, cudaStream_t st) {
     if (level < 0 || level >= c->nQ) { set_error("level out of range"); return -1; }
     if (nb_rescales < 0 || nb_rescales > level) { set_error("cannot Rescale: input Ciphertext level is too low"); return -1; }
     if (check_evk(c, level, rlk)) return -1;
@@ -640,6 +675,7 @@ int ckks_mulrelin_rescale(const Ctx* c, int level, const u64* ctA, const u64* ct
         p.limbs = c->d_limbs;
         p.a0 = ctA; p.a1 = ctA + nq * N; p.b0 = ctB; p.b1 = ctB + nq * N; p.in_rs = N; p.in_bs = ct_stride;
         p.d0 = d0; p.d1 = d1; p.d2 = d2; p.out_rs = N; p.out_bs = nq * N; p.n = c->N;
+        ProfScope ps(LGPU_KCLASS_TENSOR, st, 8.0 * c->N * nq * batch * 7, 1);
         dim3 grid((c->N / 2 + 255) / 256, (unsigned)nq, batch);
         ckks_tensor_kernel<<<grid, 256, 0, st>>>(p);
         LGPU_CUDA_OK(cudaGetLastError());

@@ -132,6 +132,17 @@ int launch_modup_qp(const Ctx* c, bool toP, int levelQ, int levelP, CSpan in, Sp
 int launch_decompose_and_split(const Ctx* c, int levelQ, int levelP, int nbPi, int digit, CSpan p0Q, Span p1Q, Span p1P,
                                int batch, cudaStream_t st);
 
+// prof.cu: launch accounting + optional event profiling (kernel classes = LGPU_KCLASS_* of the public header)
+void count_launch(int n);
+class ProfScope {
+  public:
+    ProfScope(int kclass, cudaStream_t st, double alg_bytes, int kernels);
+    ~ProfScope();
+  private:
+    int k_; cudaStream_t st_; bool on_; double bytes_; int kernels_;
+    cudaEvent_t a_ = nullptr, b_ = nullptr;
+};
+
 // capi.cu helpers
 int make_rowmap(const Ctx& c, int ring, int level, RowMap& rm);
 int make_rowmap_single(const Ctx& c, int ring, int limb, RowMap& rm);

@@ -15,6 +15,7 @@
 // Arithmetic: butterflies are the reference's lazy Montgomery butterflies (ring/ntt.go:155-171) with the
 // reference's own 4q-correction schedule, so NTT_EXACT_LAZY reproduces NTTLazy's representative in [0, 6q)
 // bit for bit; NTT_CANONICAL appends the BRedAdd pass (ring/ntt.go:174-177) in the store epilogue.
+#include "../../include/lattigo_b200.h"
 #include "engine.h"
 #include "modarith.cuh"
 
@@ -329,6 +330,7 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     p.logN = c->logN; p.mode = mode; p.ci = 0;
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
+    ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * rm.nrows * batch, s1 > 0 ? 2 : 1);
     if (s1 > 0 && launch_strided<false>(s1, p, rm.nrows, batch, st)) return -1;
     dim3 grid(1u << s1, rm.nrows, batch);
     return launch_chunk_dyn(cl, false, p, grid, st);
@@ -343,6 +345,7 @@ int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, i
     p.logN = c->logN; p.mode = mode; p.ci = 0;
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
+    ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * rm.nrows * batch, s1 > 0 ? 2 : 1);
     dim3 grid(1u << s1, rm.nrows, batch);
     if (launch_chunk_dyn(cl, true, p, grid, st)) return -1;
     if (s1 > 0) {

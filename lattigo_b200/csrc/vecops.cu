@@ -136,6 +136,8 @@ int launch_vecop(const Ctx* c, const RowMap& rm, int op, CSpan p1, CSpan p2, Spa
     const bool vec2 = (n % 2 == 0) && al(p3.p, p3.row_stride, p3.batch_stride) &&
                       (!op_uses_p1(op) || al(p1.p, p1.row_stride, p1.batch_stride)) &&
                       (!op_uses_p2(op) || al(p2.p, p2.row_stride, p2.batch_stride));
+    const int nops = 1 + (op_uses_p1(op) ? 1 : 0) + (op_uses_p2(op) ? 1 : 0) + (op_reads_p3(op) ? 1 : 0);
+    ProfScope ps(LGPU_KCLASS_VECOP, st, 8.0 * n * rm.nrows * batch * nops, 1);
     switch (op) {
 #define CASE(OPC) case OPC: return launch_one<OPC>(p, rm.nrows, batch, vec2, st);
         CASE(LGPU_OP_ADD) CASE(LGPU_OP_ADDLAZY) CASE(LGPU_OP_SUB) CASE(LGPU_OP_SUBLAZY) CASE(LGPU_OP_NEG)
