@@ -125,10 +125,8 @@ int lgpu_ring_set_roots(lgpu_ctx* ctx, int ring, int limb, const uint64_t* roots
     s.ninv = ninv;
     if (c.device >= 0) {
         LGPU_CUDA_OK(cudaSetDevice(c.device));
-        LGPU_CUDA_OK(cudaStreamSynchronize(c.stream));
-        LGPU_CUDA_OK(cudaMemcpy((void*)c.h_limbs[g].roots_fwd, roots_fwd, half * sizeof(u64), cudaMemcpyHostToDevice));
-        LGPU_CUDA_OK(cudaMemcpy((void*)c.h_limbs[g].roots_bwd, roots_bwd, half * sizeof(u64), cudaMemcpyHostToDevice));
-        c.h_limbs[g].ninv = ninv;
+        LGPU_CUDA_OK(cudaDeviceSynchronize());
+        if (upload_limb_tables(&c, g)) return -1;
         LGPU_CUDA_OK(cudaMemcpy(c.d_limbs + g, &c.h_limbs[g], sizeof(LimbConst), cudaMemcpyHostToDevice));
     }
     return 0;

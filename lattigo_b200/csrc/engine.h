@@ -29,6 +29,14 @@ struct LimbConst {
     u64 ninv;     // NInv = MForm(N^-1 mod q)
     const u64* roots_fwd;  // RootsForward  (device, NthRoot/2 entries)
     const u64* roots_bwd;  // RootsBackward (device)
+    // ---- free-form fast path (canonical outputs only; see ntt.cu) ----
+    const ulonglong2* tw_fwd;  // {psi^j, floor(psi^j * 2^64 / q)} (plain, not Montgomery), same bit-reversed indexing
+    const ulonglong2* tw_bwd;  // {psi^-j, floor(.)}
+    ulonglong2 ninv_s;         // {N^-1, floor(N^-1 * 2^64 / q)}
+    ulonglong2 last_inv_s;     // {psi^-(N/2)... = tw_bwd[1] * N^-1, floor(.)}: last inverse stage with the scaling folded in
+    u64 kq;                    // K*q, K the largest power of two with K*q <= 2^63 (forward lazy correction)
+    unsigned int fwd_mask;     // bit s: correct U (if U >= kq: U -= kq) before stage s of the forward transform
+    unsigned int inv_lazy;     // 1: q * 2^(logN+1) < 2^64 -> the inverse transform needs no per-stage correction
 };
 
 // Which global limb each row of a launch uses.
@@ -41,6 +49,7 @@ struct RowMap {
 struct HostSubRing {
     u64 q, qinv, bred_hi, bred_lo, ninv, primitive_root;
     std::vector<u64> roots_fwd, roots_bwd;  // host copies (also returned through the C ABI for cross-checks)
+    u64* d_tw = nullptr;                    // device: tw_fwd (2*half words) followed by tw_bwd
 };
 
 // ring.ModUpConstants for a (source chain, target chain) pair -- ring/basis_extension.go:90-98.
@@ -61,6 +70,7 @@ struct Ctx {
     // device tables
     LimbConst* d_limbs = nullptr;
     u64* d_roots = nullptr;        // 2 * (nQ+nP) * (nthroot/2) words
+    u64* d_tw = nullptr;           // Shoup twiddle pairs: 4 * (nQ+nP) * (nthroot/2) words
     std::vector<LimbConst> h_limbs;
     // rescale constants, ring/ring.go:329-346: rescale[(j-1)*nQ + i] = MForm(q_i - q_j^-1 mod q_i)  (Q ring)
     std::vector<u64> rescaleQ, rescaleP;
@@ -103,6 +113,8 @@ u64 h_mform(u64 a, u64 q);   // a * 2^64 mod q
 int build_context(Ctx* c, int device, int logN, int ring_type, const u64* q, int nq, const u64* p, int np);
 void destroy_context(Ctx* c);
 int ensure_scratch(Ctx* c, size_t words);
+// (re)derives the fast-path tables of global limb g from its Montgomery root tables and uploads them
+int upload_limb_tables(Ctx* c, int g);
 // half modulus of the product of `mods[0..n)` reduced mod m: floor(prod/2) mod m
 u64 h_half_prod_mod(const u64* mods, int n, u64 m);
 
@@ -119,7 +131,7 @@ struct CSpan {
     size_t batch_stride;
 };
 
-enum NttMode { NTT_CANONICAL = 0, NTT_EXACT_LAZY = 1 };
+enum NttMode { NTT_CANONICAL = 0, NTT_EXACT_LAZY = 1, NTT_REFERENCE_ARITH = 2 };
 
 int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st);
 int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st);

@@ -12,9 +12,16 @@
 // Every element crosses HBM twice per transform when logN > 12 (the intermediate stays L2-resident for
 // working sets below ~100 MB), once when logN <= 12.
 //
-// Arithmetic: butterflies are the reference's lazy Montgomery butterflies (ring/ntt.go:155-171) with the
-// reference's own 4q-correction schedule, so NTT_EXACT_LAZY reproduces NTTLazy's representative in [0, 6q)
-// bit for bit; NTT_CANONICAL appends the BRedAdd pass (ring/ntt.go:174-177) in the store epilogue.
+// Arithmetic, two variants selected at compile time (template parameter FAST):
+//   FAST = false : the reference's lazy Montgomery butterflies (ring/ntt.go:155-171) with the reference's own
+//                  4q-correction schedule, so NTT_EXACT_LAZY reproduces NTTLazy's representative in [0, 6q)
+//                  bit for bit (used only when a caller asks for the Lazy API).
+//   FAST = true  : free-form path for canonical outputs (NTT / INTT / INTTLazy for N >= 16): Shoup products with
+//                  precomputed quotients {w, floor(w 2^64 / q)} -- 6 IMAD.WIDE + 4 IMAD per modular product instead
+//                  of ~17 IMAD-class instructions for MRedLazy -- Harvey-style lazy ranges whose correction schedule
+//                  is computed per prime (none at all for primes below 2^58), the forward output canonicalised by one
+//                  Barrett pass in the store epilogue, the inverse's N^-1 folded into its last stage. The canonical
+//                  residue is unique, so the result is bit-identical to the reference's NTTStandard / INTTStandard.
 #include "../../include/lattigo_b200.h"
 #include "engine.h"
 #include "modarith.cuh"
@@ -53,10 +60,39 @@ __device__ __forceinline__ void inv_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qin
     Y = mred_lazy(U + (q << 2) - V, psi, q, qinv);
 }
 
+// ---- FAST path primitives ---------------------------------------------------------------------------
+// x*w mod q in [0, 2q) for any x < 2^64, given wp = floor(w * 2^64 / q)
+__device__ __forceinline__ u64 shoup_mul(u64 x, ulonglong2 w, u64 q) { return x * w.x - __umul64hi(x, w.y) * q; }
+
+// CT butterfly: X = U + V*w, Y = U - V*w + 2q (lazy). nq = -q mod 2^64. The sum U + V*w - hi*q is accumulated in
+// the multiplier's addend so that no separate 64-bit additions are issued for X.
+__device__ __forceinline__ void fast_fwd_bfly(u64& X, u64& Y, ulonglong2 w, u64 nq, u64 twoq, u64 kq, bool corr) {
+    u64 U = X;
+    if (corr) U = (U >= kq) ? U - kq : U;
+    const u64 V = Y;
+    const u64 hi = __umul64hi(V, w.y);
+    const u32 v0 = (u32)V, v1 = (u32)(V >> 32), w0 = (u32)w.x, w1 = (u32)(w.x >> 32);
+    const u32 h0 = (u32)hi, h1 = (u32)(hi >> 32), n0 = (u32)nq, n1 = (u32)(nq >> 32);
+    u64 acc = U + (u64)v0 * w0;
+    acc += (u64)h0 * n0;
+    const u32 t = v0 * w1 + v1 * w0 + h0 * n1 + h1 * n0;
+    acc += (u64)t << 32;
+    X = acc;
+    Y = (U << 1) + twoq - acc;
+}
+// GS butterfly: X = U + V (optionally corrected to [0, 2q)), Y = (U - V + addq) * w in [0, 2q)
+__device__ __forceinline__ void fast_inv_bfly(u64& X, u64& Y, ulonglong2 w, u64 q, u64 addq, bool corr) {
+    const u64 U = X, V = Y;
+    u64 s = U + V;
+    if (corr) { const u64 twoq = q << 1; s = (s >= twoq) ? s - twoq : s; }
+    X = s;
+    Y = shoup_mul(U - V + addq, w, q);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // strided pass: global stages [0, RL). Thread l handles elements {k * (N >> RL) + l}.
 // ---------------------------------------------------------------------------------------------------
-template <int RL, bool INVERSE>
+template <int RL, bool INVERSE, bool FAST>
 __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
     constexpr int R = 1 << RL;
     const int b = blockIdx.z;
@@ -72,7 +108,7 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
     u64 x[R];
 #pragma unroll
     for (int k = 0; k < R; k++) x[k] = in[(size_t)k * stride + l];
-    if (!INVERSE) {
+    if constexpr (!INVERSE && !FAST) {
         const u64* roots = L.roots_fwd;
 #pragma unroll
         for (int u = 0; u < RL; u++) {
@@ -85,8 +121,21 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
                 fwd_bfly(x[k], x[k + half], tw, q, qinv, red);
             }
         }
-        if (p.mode == NTT_CANONICAL && RL == 0) {}
-    } else {
+    } else if constexpr (!INVERSE && FAST) {
+        const ulonglong2* tw = L.tw_fwd;
+        const u64 nq = 0ull - q, twoq = q << 1;
+#pragma unroll
+        for (int u = 0; u < RL; u++) {
+            const int half = 1 << (RL - 1 - u);
+            const bool corr = (L.fwd_mask >> u) & 1u;
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                const ulonglong2 w = __ldg(tw + (1 << u) + (k >> (RL - u)));
+                fast_fwd_bfly(x[k], x[k + half], w, nq, twoq, L.kq, corr);
+            }
+        }
+    } else if constexpr (INVERSE && !FAST) {
         const u64* roots = L.roots_bwd;
 #pragma unroll
         for (int u = RL - 1; u >= 0; u--) {
@@ -101,6 +150,34 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
         // x N^-1 (Montgomery), canonical: ring/ntt.go:185-206 (mulscalarmontgomeryvec, also for the Lazy API when N >= 16)
 #pragma unroll
         for (int k = 0; k < R; k++) x[k] = mred(x[k], L.ninv, q, qinv);
+    } else {
+        const ulonglong2* tw = L.tw_bwd;
+        const bool lazy = L.inv_lazy != 0;
+        const int cl = p.logN - RL;   // stages already done by the chunk pass
+#pragma unroll
+        for (int u = RL - 1; u >= 1; u--) {
+            const int half = 1 << (RL - 1 - u);
+            // stage index counted from the first inverse stage: cl + (RL-1-u); inputs are < 2^(idx+1) q when lazy
+            const u64 addq = lazy ? (q << (cl + (RL - 1 - u) + 1)) : (q << 1);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                const ulonglong2 w = __ldg(tw + (1 << u) + (k >> (RL - u)));
+                fast_inv_bfly(x[k], x[k + half], w, q, addq, !lazy);
+            }
+        }
+        {   // last stage (u = 0) with N^-1 folded in: X = (U + V) * N^-1, Y = (U - V) * (w * N^-1); canonical outputs
+            constexpr int half = 1 << (RL - 1);
+            const u64 addq = lazy ? (q << p.logN) : (q << 1);
+#pragma unroll
+            for (int k = 0; k < half; k++) {
+                const u64 U = x[k], V = x[k + half];
+                const u64 a = shoup_mul(U + V, L.ninv_s, q);
+                const u64 c = shoup_mul(U - V + addq, L.last_inv_s, q);
+                x[k] = a >= q ? a - q : a;
+                x[k + half] = c >= q ? c - q : c;
+            }
+        }
     }
 #pragma unroll
     for (int k = 0; k < R; k++) out[(size_t)k * stride + l] = x[k];
@@ -126,9 +203,13 @@ __host__ __device__ constexpr int num_rounds(int cl) { return cl >= 9 ? 3 : (cl 
 __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 
 // One register round of the forward transform on chunk-local stages [A, A+RB).
-template <int CL, int A, int RB, bool FROM_GLOBAL>
-__device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const u64* roots, u64 q, u64 qinv,
+template <int CL, int A, int RB, bool FROM_GLOBAL, bool FAST>
+__device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const LimbConst& L,
                                           int s1, int logN, int chunk, int tid) {
+    const u64 q = L.q, qinv = L.qinv;
+    const u64* roots = L.roots_fwd;
+    const ulonglong2* twp = L.tw_fwd;
+    const u64 nq = 0ull - q, twoq = q << 1;
     constexpr int G = 16 >> RB;          // groups per thread
     constexpr int RR = 1 << RB;          // elements per group
     constexpr int LOB = CL - A - RB;     // bits of `lo`
@@ -147,13 +228,23 @@ __device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const u64* r
         for (int u = 0; u < RB; u++) {
             const int half = 1 << (RB - 1 - u);
             const int s = s1 + A + u;
-            const bool red = fwd_reduce_flag(s, logN);
             const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+            if constexpr (FAST) {
+                const bool corr = (L.fwd_mask >> s) & 1u;
 #pragma unroll
-            for (int k = 0; k < RR; k++) {
-                if (k & half) continue;
-                u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
-                fwd_bfly(x[k], x[k + half], tw, q, qinv, red);
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    const ulonglong2 w = __ldg(twp + twbase + (k >> (RB - u)));
+                    fast_fwd_bfly(x[k], x[k + half], w, nq, twoq, L.kq, corr);
+                }
+            } else {
+                const bool red = fwd_reduce_flag(s, logN);
+#pragma unroll
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
+                    fwd_bfly(x[k], x[k + half], tw, q, qinv, red);
+                }
             }
         }
 #pragma unroll
@@ -162,9 +253,13 @@ __device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const u64* r
 }
 
 // One register round of the inverse transform (GS) on chunk-local stages [A, A+RB), processed deepest first.
-template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE>
-__device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const u64* roots, u64 q, u64 qinv, u64 ninv,
+template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE, bool FAST>
+__device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const LimbConst& L,
                                           int s1, int chunk, int tid) {
+    const u64 q = L.q, qinv = L.qinv, ninv = L.ninv;
+    const u64* roots = L.roots_bwd;
+    const ulonglong2* twp = L.tw_bwd;
+    const bool lazy = L.inv_lazy != 0;
     constexpr int G = 16 >> RB;
     constexpr int RR = 1 << RB;
     constexpr int LOB = CL - A - RB;
@@ -181,23 +276,49 @@ __device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const u64* roots, 
             const int half = 1 << (RB - 1 - u);
             const int s = s1 + A + u;
             const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+            if constexpr (FAST) {
+                // `done` inverse stages precede this one; lazy inputs are < 2^(done+1) q
+                const int done = (CL - 1) - (A + u);
+                if (SCALE && A + u == 0) {
+                    // very last stage of a single-pass transform: fold N^-1, canonical outputs
+                    const u64 addq = lazy ? (q << (done + 1)) : (q << 1);
 #pragma unroll
-            for (int k = 0; k < RR; k++) {
-                if (k & half) continue;
-                u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
-                inv_bfly(x[k], x[k + half], tw, q, qinv);
+                    for (int k = 0; k < RR; k++) {
+                        if (k & half) continue;
+                        const u64 U = x[k], V = x[k + half];
+                        const u64 a = shoup_mul(U + V, L.ninv_s, q);
+                        const u64 c = shoup_mul(U - V + addq, L.last_inv_s, q);
+                        x[k] = a >= q ? a - q : a;
+                        x[k + half] = c >= q ? c - q : c;
+                    }
+                } else {
+                    const u64 addq = lazy ? (q << (done + 1)) : (q << 1);
+#pragma unroll
+                    for (int k = 0; k < RR; k++) {
+                        if (k & half) continue;
+                        const ulonglong2 w = __ldg(twp + twbase + (k >> (RB - u)));
+                        fast_inv_bfly(x[k], x[k + half], w, q, addq, !lazy);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
+                    inv_bfly(x[k], x[k + half], tw, q, qinv);
+                }
             }
         }
 #pragma unroll
         for (int k = 0; k < RR; k++) {
             const int idx = base + (k << LOB);
-            if (TO_GLOBAL) gdst[idx] = SCALE ? mred(x[k], ninv, q, qinv) : x[k];
+            if (TO_GLOBAL) gdst[idx] = (SCALE && !FAST) ? mred(x[k], ninv, q, qinv) : x[k];
             else sm[pad_idx(idx)] = x[k];
         }
     }
 }
 
-template <int CL>
+template <int CL, bool FAST>
 __global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1)
 ntt_chunk_fwd_kernel(NttParams p) {
     constexpr int C = 1 << CL;
@@ -212,18 +333,18 @@ ntt_chunk_fwd_kernel(NttParams p) {
     const u64* src = (s1 > 0 ? (const u64*)p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs
                              : p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs) + ((size_t)chunk << CL);
     u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
-    const u64 q = L.q, qinv = L.qinv;
-    fwd_round<CL, 0, R0, true>(sm, src, L.roots_fwd, q, qinv, s1, p.logN, chunk, tid);
+    const u64 q = L.q;
+    fwd_round<CL, 0, R0, true, FAST>(sm, src, L, s1, p.logN, chunk, tid);
     __syncthreads();
     if constexpr (R1 > 0) {
-        fwd_round<CL, R0, R1, false>(sm, nullptr, L.roots_fwd, q, qinv, s1, p.logN, chunk, tid);
+        fwd_round<CL, R0, R1, false, FAST>(sm, nullptr, L, s1, p.logN, chunk, tid);
         __syncthreads();
     }
     if constexpr (R2 > 0) {
-        fwd_round<CL, R0 + R1, R2, false>(sm, nullptr, L.roots_fwd, q, qinv, s1, p.logN, chunk, tid);
+        fwd_round<CL, R0 + R1, R2, false, FAST>(sm, nullptr, L, s1, p.logN, chunk, tid);
         __syncthreads();
     }
-    const bool canon = (p.mode == NTT_CANONICAL);
+    const bool canon = FAST || (p.mode == NTT_CANONICAL);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int idx = k * T + tid;
@@ -233,7 +354,7 @@ ntt_chunk_fwd_kernel(NttParams p) {
     }
 }
 
-template <int CL>
+template <int CL, bool FAST>
 __global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1)
 ntt_chunk_inv_kernel(NttParams p) {
     constexpr int C = 1 << CL;
@@ -247,7 +368,6 @@ ntt_chunk_inv_kernel(NttParams p) {
     const int s1 = p.logN - CL;
     const u64* src = p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs + ((size_t)chunk << CL);
     u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
-    const u64 q = L.q, qinv = L.qinv;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int idx = k * T + tid;
@@ -256,59 +376,59 @@ ntt_chunk_inv_kernel(NttParams p) {
     __syncthreads();
     // deepest round first
     if constexpr (NR == 3) {
-        inv_round<CL, R0 + R1, R2, false, false>(sm, nullptr, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
+        inv_round<CL, R0 + R1, R2, false, false, FAST>(sm, nullptr, L, s1, chunk, tid);
         __syncthreads();
     }
     if constexpr (NR >= 2) {
-        inv_round<CL, R0, R1, false, false>(sm, nullptr, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
+        inv_round<CL, R0, R1, false, false, FAST>(sm, nullptr, L, s1, chunk, tid);
         __syncthreads();
     }
-    if (s1 == 0) inv_round<CL, 0, R0, true, true>(sm, dst, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
-    else         inv_round<CL, 0, R0, true, false>(sm, dst, L.roots_bwd, q, qinv, L.ninv, s1, chunk, tid);
+    if (s1 == 0) inv_round<CL, 0, R0, true, true, FAST>(sm, dst, L, s1, chunk, tid);
+    else         inv_round<CL, 0, R0, true, false, FAST>(sm, dst, L, s1, chunk, tid);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------
 template <int CL>
-static int launch_chunk(bool inverse, const NttParams& p, dim3 grid, cudaStream_t st) {
+static int launch_chunk(bool inverse, bool fast, const NttParams& p, dim3 grid, cudaStream_t st) {
     constexpr int C = 1 << CL;
     constexpr int T = C >= 16 ? C / 16 : 1;
     size_t smem = (size_t)(C + (C >> 4) + 1) * sizeof(u64);
-    if (inverse) ntt_chunk_inv_kernel<CL><<<grid, T, smem, st>>>(p);
-    else         ntt_chunk_fwd_kernel<CL><<<grid, T, smem, st>>>(p);
+    if (inverse) { if (fast) ntt_chunk_inv_kernel<CL, true><<<grid, T, smem, st>>>(p); else ntt_chunk_inv_kernel<CL, false><<<grid, T, smem, st>>>(p); }
+    else         { if (fast) ntt_chunk_fwd_kernel<CL, true><<<grid, T, smem, st>>>(p); else ntt_chunk_fwd_kernel<CL, false><<<grid, T, smem, st>>>(p); }
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-static int launch_chunk_dyn(int cl, bool inverse, const NttParams& p, dim3 grid, cudaStream_t st) {
+static int launch_chunk_dyn(int cl, bool inverse, bool fast, const NttParams& p, dim3 grid, cudaStream_t st) {
     switch (cl) {
-        case 4: return launch_chunk<4>(inverse, p, grid, st);
-        case 5: return launch_chunk<5>(inverse, p, grid, st);
-        case 6: return launch_chunk<6>(inverse, p, grid, st);
-        case 7: return launch_chunk<7>(inverse, p, grid, st);
-        case 8: return launch_chunk<8>(inverse, p, grid, st);
-        case 9: return launch_chunk<9>(inverse, p, grid, st);
-        case 10: return launch_chunk<10>(inverse, p, grid, st);
-        case 11: return launch_chunk<11>(inverse, p, grid, st);
-        case 12: return launch_chunk<12>(inverse, p, grid, st);
+        case 4: return launch_chunk<4>(inverse, fast, p, grid, st);
+        case 5: return launch_chunk<5>(inverse, fast, p, grid, st);
+        case 6: return launch_chunk<6>(inverse, fast, p, grid, st);
+        case 7: return launch_chunk<7>(inverse, fast, p, grid, st);
+        case 8: return launch_chunk<8>(inverse, fast, p, grid, st);
+        case 9: return launch_chunk<9>(inverse, fast, p, grid, st);
+        case 10: return launch_chunk<10>(inverse, fast, p, grid, st);
+        case 11: return launch_chunk<11>(inverse, fast, p, grid, st);
+        case 12: return launch_chunk<12>(inverse, fast, p, grid, st);
     }
     set_error("unsupported chunk size");
     return -1;
 }
 
-template <bool INV>
+template <bool INV, bool FAST>
 static int launch_strided(int rl, const NttParams& p, int rows, int batch, cudaStream_t st) {
     const int N = 1 << p.logN;
     const int threads_total = N >> rl;
     const int bs = threads_total < 256 ? threads_total : 256;
     dim3 grid((threads_total + bs - 1) / bs, rows, batch);
     switch (rl) {
-        case 1: ntt_strided_kernel<1, INV><<<grid, bs, 0, st>>>(p); break;
-        case 2: ntt_strided_kernel<2, INV><<<grid, bs, 0, st>>>(p); break;
-        case 3: ntt_strided_kernel<3, INV><<<grid, bs, 0, st>>>(p); break;
-        case 4: ntt_strided_kernel<4, INV><<<grid, bs, 0, st>>>(p); break;
-        case 5: ntt_strided_kernel<5, INV><<<grid, bs, 0, st>>>(p); break;
+        case 1: ntt_strided_kernel<1, INV, FAST><<<grid, bs, 0, st>>>(p); break;
+        case 2: ntt_strided_kernel<2, INV, FAST><<<grid, bs, 0, st>>>(p); break;
+        case 3: ntt_strided_kernel<3, INV, FAST><<<grid, bs, 0, st>>>(p); break;
+        case 4: ntt_strided_kernel<4, INV, FAST><<<grid, bs, 0, st>>>(p); break;
+        case 5: ntt_strided_kernel<5, INV, FAST><<<grid, bs, 0, st>>>(p); break;
         default: set_error("unsupported strided radix"); return -1;
     }
     LGPU_CUDA_OK(cudaGetLastError());
@@ -331,13 +451,16 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
     ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * rm.nrows * batch, s1 > 0 ? 2 : 1);
-    if (s1 > 0 && launch_strided<false>(s1, p, rm.nrows, batch, st)) return -1;
+    const bool fast = (mode == NTT_CANONICAL);
+    if (s1 > 0 && (fast ? launch_strided<false, true>(s1, p, rm.nrows, batch, st) : launch_strided<false, false>(s1, p, rm.nrows, batch, st))) return -1;
     dim3 grid(1u << s1, rm.nrows, batch);
-    return launch_chunk_dyn(cl, false, p, grid, st);
+    return launch_chunk_dyn(cl, false, fast, p, grid, st);
 }
 
 int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
-    (void)mode;  // INTTLazy == INTT for N >= 16 (ring/ntt.go:197-206)
+    // INTTLazy == INTT for N >= 16 (ring/ntt.go:197-206): both are canonical, so both take the fast path;
+    // NTT_REFERENCE_ARITH keeps the Montgomery kernels reachable (cross-check in the tests).
+    const bool fast = (mode != NTT_REFERENCE_ARITH);
     if (check_common(c, rm, batch)) return -1;
     NttParams p;
     p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
@@ -347,12 +470,12 @@ int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, i
     const int s1 = c->logN - cl;
     ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * rm.nrows * batch, s1 > 0 ? 2 : 1);
     dim3 grid(1u << s1, rm.nrows, batch);
-    if (launch_chunk_dyn(cl, true, p, grid, st)) return -1;
+    if (launch_chunk_dyn(cl, true, fast, p, grid, st)) return -1;
     if (s1 > 0) {
         // second pass works in place on `out`
         NttParams p2 = p;
         p2.in = out.p; p2.in_rs = out.row_stride; p2.in_bs = out.batch_stride;
-        return launch_strided<true>(s1, p2, rm.nrows, batch, st);
+        return fast ? launch_strided<true, true>(s1, p2, rm.nrows, batch, st) : launch_strided<true, false>(s1, p2, rm.nrows, batch, st);
     }
     return 0;
 }

@@ -194,6 +194,50 @@ int ensure_scratch(Ctx* c, size_t words) {
     return 0;
 }
 
+static inline u64 shoup_q(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+
+int upload_limb_tables(Ctx* c, int i) {
+    const size_t half = (size_t)(c->nthroot >> 1);
+    HostSubRing& s = c->sub[i];
+    const u64 q = s.q;
+    u64* rf = c->d_roots + (size_t)(2 * i) * half;
+    u64* rb = rf + half;
+    LGPU_CUDA_OK(cudaMemcpy(rf, s.roots_fwd.data(), half * sizeof(u64), cudaMemcpyHostToDevice));
+    LGPU_CUDA_OK(cudaMemcpy(rb, s.roots_bwd.data(), half * sizeof(u64), cudaMemcpyHostToDevice));
+    // Shoup pairs derived from the (possibly caller-supplied) Montgomery tables: w = IMForm(root)
+    const u64 rinv = h_invmod(h_mform(1, q), q);   // 2^-64 mod q
+    std::vector<u64> tw(4 * half);
+    for (size_t j = 0; j < half; j++) {
+        const u64 wf = h_mulmod(s.roots_fwd[j], rinv, q), wb = h_mulmod(s.roots_bwd[j], rinv, q);
+        tw[2 * j] = wf; tw[2 * j + 1] = shoup_q(wf, q);
+        tw[2 * half + 2 * j] = wb; tw[2 * half + 2 * j + 1] = shoup_q(wb, q);
+    }
+    u64* dtw = c->d_tw + (size_t)(4 * i) * half;
+    LGPU_CUDA_OK(cudaMemcpy(dtw, tw.data(), tw.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    LimbConst& L = c->h_limbs[i];
+    L.q = q; L.qinv = s.qinv; L.bred_hi = s.bred_hi; L.bred_lo = s.bred_lo;
+    L.ninv = s.ninv; L.roots_fwd = rf; L.roots_bwd = rb;
+    L.tw_fwd = reinterpret_cast<const ulonglong2*>(dtw);
+    L.tw_bwd = reinterpret_cast<const ulonglong2*>(dtw + 2 * half);
+    const u64 ninv = h_mulmod(s.ninv, rinv, q);
+    L.ninv_s = make_ulonglong2(ninv, shoup_q(ninv, q));
+    const u64 last = h_mulmod(tw[2 * half + 2], ninv, q);   // tw_bwd[1] * N^-1
+    L.last_inv_s = make_ulonglong2(last, shoup_q(last, q));
+    // forward lazy-correction schedule: values are kept below 2K*q <= 2^64; a stage adds at most 2q.
+    u64 K = 1;
+    while ((u128)(2 * K) * q <= ((u128)1 << 63)) K *= 2;
+    L.kq = K * q;
+    unsigned mask = 0;
+    u64 b = 2 * K < 8 ? 2 * K : 8;   // assumed input bound (in units of q)
+    for (int st = 0; st < c->logN + (c->ring_type ? 1 : 0); st++) {
+        if (b + 2 > 2 * K) { mask |= 1u << st; b = K; }
+        b += 2;
+    }
+    L.fwd_mask = mask;
+    L.inv_lazy = ((u128)q << (c->logN + 1)) < ((u128)1 << 64) ? 1u : 0u;
+    return 0;
+}
+
 int build_context(Ctx* c, int device, int logN, int ring_type, const u64* q, int nq, const u64* p, int np) {
     if (logN < 4 || logN > 17) { set_error("invalid ring degree: need 16 <= N <= 2^17"); return -1; }
     if (nq <= 0 || !q) { set_error("invalid ModuliChain (must be non-empty)"); return -1; }
@@ -277,15 +321,10 @@ int build_context(Ctx* c, int device, int logN, int ring_type, const u64* q, int
     LGPU_CUDA_OK(cudaSetDevice(device));
     const size_t half = (size_t)(c->nthroot >> 1);
     LGPU_CUDA_OK(cudaMalloc(&c->d_roots, 2 * (size_t)nl * half * sizeof(u64)));
+    LGPU_CUDA_OK(cudaMalloc(&c->d_tw, 4 * (size_t)nl * half * sizeof(u64)));
     c->h_limbs.resize(nl);
     for (int i = 0; i < nl; i++) {
-        u64* rf = c->d_roots + (size_t)(2 * i) * half;
-        u64* rb = rf + half;
-        LGPU_CUDA_OK(cudaMemcpy(rf, c->sub[i].roots_fwd.data(), half * sizeof(u64), cudaMemcpyHostToDevice));
-        LGPU_CUDA_OK(cudaMemcpy(rb, c->sub[i].roots_bwd.data(), half * sizeof(u64), cudaMemcpyHostToDevice));
-        LimbConst& L = c->h_limbs[i];
-        L.q = c->sub[i].q; L.qinv = c->sub[i].qinv; L.bred_hi = c->sub[i].bred_hi; L.bred_lo = c->sub[i].bred_lo;
-        L.ninv = c->sub[i].ninv; L.roots_fwd = rf; L.roots_bwd = rb;
+        if (upload_limb_tables(c, i)) return -1;
     }
     LGPU_CUDA_OK(cudaMalloc(&c->d_limbs, nl * sizeof(LimbConst)));
     LGPU_CUDA_OK(cudaMemcpy(c->d_limbs, c->h_limbs.data(), nl * sizeof(LimbConst), cudaMemcpyHostToDevice));
@@ -306,6 +345,7 @@ void destroy_context(Ctx* c) {
     cudaFree(c->d_blob);
     cudaFree(c->d_limbs);
     cudaFree(c->d_roots);
+    cudaFree(c->d_tw);
 }
 
 }  // namespace lgpu

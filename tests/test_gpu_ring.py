@@ -38,12 +38,19 @@ def test_golden_vectors_through_gpu():
         ctx.close()
 
 
+@pytest.mark.parametrize("primes", ["q61", "q45_56"])
 @pytest.mark.parametrize("logN", [4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17])
-def test_ntt_matches_oracle_all_sizes(logN):
-    """Covers every chunk-size instantiation and every strided radix. C1 is logN=12."""
+def test_ntt_matches_oracle_all_sizes(logN, primes):
+    """Covers every chunk-size instantiation and every strided radix (C1 is logN=12), with 61-bit primes (lazy
+    corrections every other stage, corrected inverse) and with CKKS-sized 45/55/56-bit primes (no forward
+    correction at all, correction-free inverse for the 45-bit ones)."""
     lb = _lb()
     N = 1 << logN
-    Q = H.Qi60[:3]
+    if primes == "q61":
+        Q = H.Qi60[:3]
+    else:
+        q, p = O.gen_moduli(logN + 1, [56, 45, 45], [55])
+        Q = [q[1], q[0], p[0]]
     ctx = lb.Context(logN, Q)
     ring = O.Ring(N, Q)
     rng = np.random.default_rng(100 + logN)
