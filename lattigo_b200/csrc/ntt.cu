@@ -92,7 +92,7 @@ __device__ __forceinline__ void fast_inv_bfly(u64& X, u64& Y, ulonglong2 w, u64 
 // ---------------------------------------------------------------------------------------------------
 // strided pass: global stages [0, RL). Thread l handles elements {k * (N >> RL) + l}.
 // ---------------------------------------------------------------------------------------------------
-template <int RL, bool INVERSE, bool FAST>
+template <int RL, bool INVERSE, int FAST>
 __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
     constexpr int R = 1 << RL;
     const int b = blockIdx.z;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
 #pragma unroll
         for (int u = 0; u < RL; u++) {
             const int half = 1 << (RL - 1 - u);
-            const bool corr = (L.fwd_mask >> u) & 1u;
+            const bool corr = (FAST == 1) && ((L.fwd_mask >> u) & 1u);
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 if (k & half) continue;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
         for (int k = 0; k < R; k++) x[k] = mred(x[k], L.ninv, q, qinv);
     } else {
         const ulonglong2* tw = L.tw_bwd;
-        const bool lazy = L.inv_lazy != 0;
+        const bool lazy = (FAST == 2) || (FAST == 1 && L.inv_lazy != 0);
         const int cl = p.logN - RL;   // stages already done by the chunk pass
 #pragma unroll
         for (int u = RL - 1; u >= 1; u--) {
@@ -203,7 +203,7 @@ __host__ __device__ constexpr int num_rounds(int cl) { return cl >= 9 ? 3 : (cl 
 __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 
 // One register round of the forward transform on chunk-local stages [A, A+RB).
-template <int CL, int A, int RB, bool FROM_GLOBAL, bool FAST>
+template <int CL, int A, int RB, bool FROM_GLOBAL, int FAST>
 __device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const LimbConst& L,
                                           int s1, int logN, int chunk, int tid) {
     const u64 q = L.q, qinv = L.qinv;
@@ -230,7 +230,7 @@ __device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const LimbCo
             const int s = s1 + A + u;
             const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
             if constexpr (FAST) {
-                const bool corr = (L.fwd_mask >> s) & 1u;
+                const bool corr = (FAST == 1) && ((L.fwd_mask >> s) & 1u);
 #pragma unroll
                 for (int k = 0; k < RR; k++) {
                     if (k & half) continue;
@@ -253,7 +253,7 @@ __device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const LimbCo
 }
 
 // One register round of the inverse transform (GS) on chunk-local stages [A, A+RB), processed deepest first.
-template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE, bool FAST>
+template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE, int FAST>
 __device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const LimbConst& L,
                                           int s1, int chunk, int tid) {
     const u64 q = L.q, qinv = L.qinv, ninv = L.ninv;
@@ -312,13 +312,13 @@ __device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const LimbConst& L
 #pragma unroll
         for (int k = 0; k < RR; k++) {
             const int idx = base + (k << LOB);
-            if (TO_GLOBAL) gdst[idx] = (SCALE && !FAST) ? mred(x[k], ninv, q, qinv) : x[k];
+            if (TO_GLOBAL) gdst[idx] = (SCALE && FAST == 0) ? mred(x[k], ninv, q, qinv) : x[k];
             else sm[pad_idx(idx)] = x[k];
         }
     }
 }
 
-template <int CL, bool FAST>
+template <int CL, int FAST>
 __global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1)
 ntt_chunk_fwd_kernel(NttParams p) {
     constexpr int C = 1 << CL;
@@ -344,7 +344,7 @@ ntt_chunk_fwd_kernel(NttParams p) {
         fwd_round<CL, R0 + R1, R2, false, FAST>(sm, nullptr, L, s1, p.logN, chunk, tid);
         __syncthreads();
     }
-    const bool canon = FAST || (p.mode == NTT_CANONICAL);
+    const bool canon = (FAST != 0) || (p.mode == NTT_CANONICAL);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int idx = k * T + tid;
@@ -354,7 +354,7 @@ ntt_chunk_fwd_kernel(NttParams p) {
     }
 }
 
-template <int CL, bool FAST>
+template <int CL, int FAST>
 __global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1)
 ntt_chunk_inv_kernel(NttParams p) {
     constexpr int C = 1 << CL;
@@ -391,17 +391,24 @@ ntt_chunk_inv_kernel(NttParams p) {
 // host launchers
 // ---------------------------------------------------------------------------------------------------
 template <int CL>
-static int launch_chunk(bool inverse, bool fast, const NttParams& p, dim3 grid, cudaStream_t st) {
+static int launch_chunk(bool inverse, int fast, const NttParams& p, dim3 grid, cudaStream_t st) {
     constexpr int C = 1 << CL;
     constexpr int T = C >= 16 ? C / 16 : 1;
     size_t smem = (size_t)(C + (C >> 4) + 1) * sizeof(u64);
-    if (inverse) { if (fast) ntt_chunk_inv_kernel<CL, true><<<grid, T, smem, st>>>(p); else ntt_chunk_inv_kernel<CL, false><<<grid, T, smem, st>>>(p); }
-    else         { if (fast) ntt_chunk_fwd_kernel<CL, true><<<grid, T, smem, st>>>(p); else ntt_chunk_fwd_kernel<CL, false><<<grid, T, smem, st>>>(p); }
+    if (inverse) {
+        if (fast == 2) ntt_chunk_inv_kernel<CL, 2><<<grid, T, smem, st>>>(p);
+        else if (fast == 1) ntt_chunk_inv_kernel<CL, 1><<<grid, T, smem, st>>>(p);
+        else ntt_chunk_inv_kernel<CL, 0><<<grid, T, smem, st>>>(p);
+    } else {
+        if (fast == 2) ntt_chunk_fwd_kernel<CL, 2><<<grid, T, smem, st>>>(p);
+        else if (fast == 1) ntt_chunk_fwd_kernel<CL, 1><<<grid, T, smem, st>>>(p);
+        else ntt_chunk_fwd_kernel<CL, 0><<<grid, T, smem, st>>>(p);
+    }
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-static int launch_chunk_dyn(int cl, bool inverse, bool fast, const NttParams& p, dim3 grid, cudaStream_t st) {
+static int launch_chunk_dyn(int cl, bool inverse, int fast, const NttParams& p, dim3 grid, cudaStream_t st) {
     switch (cl) {
         case 4: return launch_chunk<4>(inverse, fast, p, grid, st);
         case 5: return launch_chunk<5>(inverse, fast, p, grid, st);
@@ -417,7 +424,7 @@ static int launch_chunk_dyn(int cl, bool inverse, bool fast, const NttParams& p,
     return -1;
 }
 
-template <bool INV, bool FAST>
+template <bool INV, int FAST>
 static int launch_strided(int rl, const NttParams& p, int rows, int batch, cudaStream_t st) {
     const int N = 1 << p.logN;
     const int threads_total = N >> rl;
@@ -433,6 +440,16 @@ static int launch_strided(int rl, const NttParams& p, int rows, int batch, cudaS
     }
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// 2 = every limb of the launch needs no lazy correction at all (forward: fwd_mask == 0; inverse: inv_lazy), so the
+// correction code is compiled out; 1 = per-limb schedules evaluated at run time.
+static int fast_variant(const Ctx* c, const RowMap& rm, bool inverse) {
+    for (int r = 0; r < rm.nrows; r++) {
+        const LimbConst& L = c->h_limbs[rm.limb[r]];
+        if (inverse ? (L.inv_lazy == 0) : (L.fwd_mask != 0)) return 1;
+    }
+    return 2;
 }
 
 static int check_common(const Ctx* c, const RowMap& rm, int batch) {
@@ -451,8 +468,13 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
     ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * rm.nrows * batch, s1 > 0 ? 2 : 1);
-    const bool fast = (mode == NTT_CANONICAL);
-    if (s1 > 0 && (fast ? launch_strided<false, true>(s1, p, rm.nrows, batch, st) : launch_strided<false, false>(s1, p, rm.nrows, batch, st))) return -1;
+    const int fast = (mode == NTT_CANONICAL) ? fast_variant(c, rm, false) : 0;
+    if (s1 > 0) {
+        int rc = fast == 2 ? launch_strided<false, 2>(s1, p, rm.nrows, batch, st)
+               : fast == 1 ? launch_strided<false, 1>(s1, p, rm.nrows, batch, st)
+                           : launch_strided<false, 0>(s1, p, rm.nrows, batch, st);
+        if (rc) return -1;
+    }
     dim3 grid(1u << s1, rm.nrows, batch);
     return launch_chunk_dyn(cl, false, fast, p, grid, st);
 }
@@ -460,7 +482,7 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
 int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
     // INTTLazy == INTT for N >= 16 (ring/ntt.go:197-206): both are canonical, so both take the fast path;
     // NTT_REFERENCE_ARITH keeps the Montgomery kernels reachable (cross-check in the tests).
-    const bool fast = (mode != NTT_REFERENCE_ARITH);
+    const int fast = (mode != NTT_REFERENCE_ARITH) ? fast_variant(c, rm, true) : 0;
     if (check_common(c, rm, batch)) return -1;
     NttParams p;
     p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
@@ -475,7 +497,9 @@ int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, i
         // second pass works in place on `out`
         NttParams p2 = p;
         p2.in = out.p; p2.in_rs = out.row_stride; p2.in_bs = out.batch_stride;
-        return fast ? launch_strided<true, true>(s1, p2, rm.nrows, batch, st) : launch_strided<true, false>(s1, p2, rm.nrows, batch, st);
+        return fast == 2 ? launch_strided<true, 2>(s1, p2, rm.nrows, batch, st)
+             : fast == 1 ? launch_strided<true, 1>(s1, p2, rm.nrows, batch, st)
+                         : launch_strided<true, 0>(s1, p2, rm.nrows, batch, st);
     }
     return 0;
 }

@@ -31,13 +31,15 @@ def timeit(fn, iters=20, warmup=3, flush=None):
 def main():
     logN, nl = 16, 44
     N = 1 << logN
-    Q = presets.QI60[:32] + presets.PI60[:12]
+    which = sys.argv[1] if len(sys.argv) > 1 else "q61"
+    Q = presets.QI60[:32] + presets.PI60[:12] if which == "q61" else presets.PRESETS["CKKS_L44"]["Q"][1:] + [presets.PRESETS["CKKS_L44"]["Q"][1] - 0] [:0] + presets.PRESETS["CKKS_L44"]["Q"][:1]
+    Q = Q[:nl]
     ctx = lb.Context(logN, Q)
     rq = ctx.ringQ
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")   # 256 MiB > L2
     S = nl * N * 8
-    print(json.dumps({"gpu": torch.cuda.get_device_name(0), "cpus": os.cpu_count()}))
-    for batch in (1, 4):
+    print(json.dumps({"gpu": torch.cuda.get_device_name(0), "cpus": os.cpu_count(), "primes": which}))
+    for batch in (1, 4, 8):
         x = torch.randint(0, 2**60, (batch, nl, N), dtype=torch.int64, device="cuda")
         y = torch.empty_like(x)
         z = torch.randint(0, 2**60, (batch, nl, N), dtype=torch.int64, device="cuda")
@@ -46,8 +48,6 @@ def main():
             ("ntt_fwd_lazy", lambda: rq.NTTLazy(x, y), 2 * S * batch),
             ("ntt_inv", lambda: rq.INTT(x, y), 2 * S * batch),
             ("mulcoeffs_montgomery", lambda: rq.MulCoeffsMontgomery(x, z, y), 3 * S * batch),
-            ("add", lambda: rq.Add(x, z, y), 3 * S * batch),
-            ("copy_torch", lambda: y.copy_(x), 2 * S * batch),
         ):
             med, best = timeit(fn, flush=flush)
             print(json.dumps({"kernel": name, "batch": batch, "limbs": nl, "logN": logN, "us_median": med * 1e6,
