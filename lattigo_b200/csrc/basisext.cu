@@ -39,8 +39,29 @@ struct ModUpParams {
     int tg;                // targets per blockIdx.y
 };
 
+// Constants of every target (q, qinv, half, the c_ji row and the vtimesqmodp row) are staged once per CTA in shared
+// memory; a thread owns one coefficient, computes y_i and v once and then streams through ALL targets (coalesced
+// row stores), so the fp64 divisions and the source loads are not repeated per target group.
 template <int NSMAX>
-__global__ void __launch_bounds__(128) modup_kernel(ModUpParams p) {
+__global__ void __launch_bounds__(256) modup_kernel(ModUpParams p) {
+    extern __shared__ u64 sm[];
+    const int nT = p.nA + p.nB;
+    const int nS = p.nS;
+    // per target t: [0] q, [1] qinv, [2] half_t, [3 .. 3+nS) c_ji, [3+nS .. 3+2nS+1) vtimesqmodp row
+    const int rec = 3 + 2 * nS + 1;
+    for (int idx = threadIdx.x; idx < nT * rec; idx += blockDim.x) {
+        const int t = idx / rec, f = idx - t * rec;
+        int limb, crow;
+        if (t < p.nA) { limb = p.limbA0 + t; crow = t; } else { limb = p.limbB0 + (t - p.nA); crow = p.crowB0 + (t - p.nA); }
+        u64 v;
+        if (f == 0) v = p.limbs[limb].q;
+        else if (f == 1) v = p.limbs[limb].qinv;
+        else if (f == 2) v = p.half_t[t];
+        else if (f < 3 + nS) v = p.blob[p.off_qoverqimodp + (size_t)crow * p.ldc + (f - 3)];
+        else v = p.blob[p.off_vtimesqmodp + (size_t)crow * p.ldv + (f - 3 - nS)];
+        sm[idx] = v;
+    }
+    __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= p.n) return;
     const int b = blockIdx.z;
@@ -50,47 +71,44 @@ __global__ void __launch_bounds__(128) modup_kernel(ModUpParams p) {
     const u64* cinv = p.blob + p.off_qoverqiinvqi;
 #pragma unroll
     for (int i = 0; i < NSMAX; i++) {
-        if (i < p.nS) {
+        if (i < nS) {
             const LimbConst& L = p.limbs[p.src_limb[i]];
             const u64 q = L.q;
             const u64 xi = src[(size_t)i * p.src_rs];
             const u64 yi = mred(xi + p.half_src[i], cinv[i], q, L.qinv);
             y[i] = yi;
             vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(yi), __ull2double_rn(q)));
+        } else {
+            y[i] = 0;
         }
     }
-    const u64 v = __double2ull_rz(vi);
-    const int nT = p.nA + p.nB;
+    const int v = (int)__double2ull_rz(vi);
     const int t0 = blockIdx.y * p.tg;
     const int t1 = min(t0 + p.tg, nT);
+#pragma unroll 2
     for (int t = t0; t < t1; t++) {
-        int limb, crow;
         u64* dst;
         if (t < p.nA) {
             if (t >= p.exlo && t < p.exhi) continue;
-            limb = p.limbA0 + t; crow = t;
             dst = p.outA + (size_t)b * p.outA_bs + (size_t)t * p.outA_rs + x;
         } else {
-            const int j = t - p.nA;
-            limb = p.limbB0 + j; crow = p.crowB0 + j;
-            dst = p.outB + (size_t)b * p.outB_bs + (size_t)j * p.outB_rs + x;
+            dst = p.outB + (size_t)b * p.outB_bs + (size_t)(t - p.nA) * p.outB_rs + x;
         }
-        const LimbConst& L = p.limbs[limb];
-        const u64 tq = L.q;
-        const u64* c = p.blob + p.off_qoverqimodp + (size_t)crow * p.ldc;
+        const u64* R = sm + t * rec;
+        const u64 tq = R[0];
         u64 rhi = 0, rlo = 0;
 #pragma unroll
         for (int i = 0; i < NSMAX; i++) {
-            if (i < p.nS) {
+            if (i < nS) {
                 u64 mhi, mlo;
-                mul128(y[i], __ldg(c + i), mhi, mlo);
+                mul128(y[i], R[3 + i], mhi, mlo);
                 rlo += mlo;
                 rhi += mhi + (rlo < mlo);
             }
         }
-        const u64 hhi = mulhi64(rlo * L.qinv, tq);
-        u64 r = rhi - hhi + tq + __ldg(p.blob + p.off_vtimesqmodp + (size_t)crow * p.ldv + v);   // multSum, :651
-        r = cred(r + tq - p.half_t[t], tq);                                                        // SubScalarBigint
+        const u64 hhi = mulhi64(rlo * R[1], tq);
+        u64 r = rhi - hhi + tq + R[3 + nS + v];     // multSum, ring/basis_extension.go:651
+        r = cred(r + tq - R[2], tq);                 // SubScalarBigint
         *dst = r;
     }
 }
@@ -122,14 +140,29 @@ __global__ void __launch_bounds__(256) decomp_single_kernel(DecompSingleParams p
     }
 }
 
+// all targets in one group (y_i and v computed once per coefficient) as soon as coefficients x batch fill the GPU
+static int target_group(const Ctx* c, int nT, int batch) {
+    const long ctas = (long)((c->N + 255) / 256) * batch;
+    if (ctas >= 4 * 148) return nT;
+    int groups = (int)((4 * 148 + ctas - 1) / ctas);
+    int tg = (nT + groups - 1) / groups;
+    return tg < 1 ? 1 : tg;
+}
+
 static int launch_modup(const ModUpParams& p, int batch, cudaStream_t st) {
     const int nT = p.nA + p.nB;
     ProfScope ps(LGPU_KCLASS_MODUP, st, 8.0 * p.n * batch * (p.nS + nT - (p.exhi - p.exlo)), 1);
-    dim3 grid((p.n + 127) / 128, (nT + p.tg - 1) / p.tg, batch);
-    if (p.nS <= 4)       modup_kernel<4><<<grid, 128, 0, st>>>(p);
-    else if (p.nS <= 8)  modup_kernel<8><<<grid, 128, 0, st>>>(p);
-    else if (p.nS <= 16) modup_kernel<16><<<grid, 128, 0, st>>>(p);
-    else                 modup_kernel<kMaxSrc><<<grid, 128, 0, st>>>(p);
+    dim3 grid((p.n + 255) / 256, (nT + p.tg - 1) / p.tg, batch);
+    const size_t smem = (size_t)nT * (3 + 2 * p.nS + 1) * sizeof(u64);
+    if (smem > 200 * 1024) { set_error("basis extension: constant set too large for shared memory"); return -1; }
+    auto go = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, 256, smem, st>>>(p);
+    };
+    if (p.nS <= 4)       go(modup_kernel<4>);
+    else if (p.nS <= 8)  go(modup_kernel<8>);
+    else if (p.nS <= 16) go(modup_kernel<16>);
+    else                 go(modup_kernel<kMaxSrc>);
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -164,7 +197,7 @@ int launch_modup_qp(const Ctx* c, bool toP, int levelQ, int levelP, CSpan in, Sp
         p.outA = out.p; p.outA_rs = out.row_stride; p.outA_bs = out.batch_stride; p.nA = nT; p.limbA0 = 0; p.exlo = p.exhi = 0;
         p.nB = 0;
     }
-    p.tg = nT <= 8 ? nT : 6;
+    p.tg = target_group(c, nT, batch);
     return launch_modup(p, batch, st);
 }
 
@@ -218,7 +251,7 @@ int launch_decompose_and_split(const Ctx* c, int levelQ, int levelP, int nbPi, i
     p.outB = p1P.p; p.outB_rs = p1P.row_stride; p.outB_bs = p1P.batch_stride; p.nB = levelP + 1; p.limbB0 = c->nQ; p.crowB0 = c->nQ;
     for (int j = 0; j <= levelQ; j++) p.half_t[j] = h_half_prod_mod(D, p.nS, c->Q[j]);
     for (int j = 0; j <= levelP; j++) p.half_t[p.nA + j] = h_half_prod_mod(D, p.nS, c->P[j]);
-    p.tg = 6;
+    p.tg = target_group(c, p.nA + p.nB, batch);
     return launch_modup(p, batch, st);
 }
 

@@ -334,6 +334,17 @@ ntt_chunk_fwd_kernel(NttParams p) {
                              : p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs) + ((size_t)chunk << CL);
     u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
     const u64 q = L.q;
+    if constexpr (FAST != 0 && CL == 12) {
+        // the last round reads 15 twiddle pairs per thread (61 KB per CTA): pull their lines into L1 now, while
+        // the first two rounds run, so the round does not start on an L2 round trip
+        const ulonglong2* tw = L.tw_fwd;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = s1 + 8 + u;
+            const ulonglong2* a = tw + (1 << s) + (chunk << (8 + u)) + (tid << u);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+        }
+    }
     fwd_round<CL, 0, R0, true, FAST>(sm, src, L, s1, p.logN, chunk, tid);
     __syncthreads();
     if constexpr (R1 > 0) {
