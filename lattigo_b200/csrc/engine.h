@@ -37,6 +37,12 @@ struct LimbConst {
     u64 kq;                    // K*q, K the largest power of two with K*q <= 2^63 (forward lazy correction)
     unsigned int fwd_mask;     // bit s: correct U (if U >= kq: U -= kq) before stage s of the forward transform
     unsigned int inv_lazy;     // 1: q * 2^(logN+1) < 2^64 -> the inverse transform needs no per-stage correction
+    // ---- FP64-pipe path (ntt_fp64.cu), primes below ~2^46 ----
+    unsigned int fp_ok;        // 1: (10 + logN) * q < 2^51 -> exact FP64 butterflies are valid for this prime
+    double fq, fqinv;          // q and fl(1/q)
+    double fninv, flast_inv;   // N^-1 mod q and psi_bwd[1] * N^-1 mod q as doubles
+    const double* ftw_fwd;     // psi^j as doubles (same bit-reversed indexing as roots_fwd)
+    const double* ftw_bwd;
 };
 
 // Which global limb each row of a launch uses.
@@ -71,6 +77,7 @@ struct Ctx {
     LimbConst* d_limbs = nullptr;
     u64* d_roots = nullptr;        // 2 * (nQ+nP) * (nthroot/2) words
     u64* d_tw = nullptr;           // Shoup twiddle pairs: 4 * (nQ+nP) * (nthroot/2) words
+    double* d_ftw = nullptr;       // FP64 twiddles: 2 * (nQ+nP) * (nthroot/2) doubles
     std::vector<LimbConst> h_limbs;
     // rescale constants, ring/ring.go:329-346: rescale[(j-1)*nQ + i] = MForm(q_i - q_j^-1 mod q_i)  (Q ring)
     std::vector<u64> rescaleQ, rescaleP;
@@ -138,6 +145,10 @@ int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, i
 
 int launch_vecop(const Ctx* c, const RowMap& rm, int op, CSpan p1, CSpan p2, Span p3, int batch,
                  const u64* h_s0, const u64* h_s1, u64 s0, u64 s1, int n, cudaStream_t st);
+
+// ntt_fp64.cu
+bool fp64_ntt_supported(const Ctx* c);
+int launch_ntt_fp64(const Ctx* c, const RowMap& rm, bool inverse, CSpan in, Span out, int batch, cudaStream_t st);
 
 // basisext.cu
 int launch_modup_qp(const Ctx* c, bool toP, int levelQ, int levelP, CSpan in, Span out, int batch, cudaStream_t st);

@@ -22,6 +22,7 @@
 //                  is computed per prime (none at all for primes below 2^58), the forward output canonicalised by one
 //                  Barrett pass in the store epilogue, the inverse's N^-1 folded into its last stage. The canonical
 //                  residue is unique, so the result is bit-identical to the reference's NTTStandard / INTTStandard.
+#include <cstdlib>
 #include "../../include/lattigo_b200.h"
 #include "engine.h"
 #include "modarith.cuh"
@@ -318,8 +319,8 @@ __device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const LimbConst& L
     }
 }
 
-template <int CL, int FAST>
-__global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1)
+template <int CL, int FAST, int MINB = 1>
+__global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1, MINB)
 ntt_chunk_fwd_kernel(NttParams p) {
     constexpr int C = 1 << CL;
     constexpr int T = C / 16;
@@ -411,7 +412,12 @@ static int launch_chunk(bool inverse, int fast, const NttParams& p, dim3 grid, c
         else if (fast == 1) ntt_chunk_inv_kernel<CL, 1><<<grid, T, smem, st>>>(p);
         else ntt_chunk_inv_kernel<CL, 0><<<grid, T, smem, st>>>(p);
     } else {
-        if (fast == 2) ntt_chunk_fwd_kernel<CL, 2><<<grid, T, smem, st>>>(p);
+        if (fast == 2) {
+            static const int minb = [] { const char* e = getenv("LGPU_NTT_MINB"); return e ? atoi(e) : 2; }();
+            if (CL == 12 && minb == 3) ntt_chunk_fwd_kernel<CL, 2, (CL == 12 ? 3 : 1)><<<grid, T, smem, st>>>(p);
+            else if (CL == 12 && minb == 4) ntt_chunk_fwd_kernel<CL, 2, (CL == 12 ? 4 : 1)><<<grid, T, smem, st>>>(p);
+            else ntt_chunk_fwd_kernel<CL, 2, (CL == 12 ? 2 : 1)><<<grid, T, smem, st>>>(p);
+        }
         else if (fast == 1) ntt_chunk_fwd_kernel<CL, 1><<<grid, T, smem, st>>>(p);
         else ntt_chunk_fwd_kernel<CL, 0><<<grid, T, smem, st>>>(p);
     }
@@ -470,7 +476,49 @@ static int check_common(const Ctx* c, const RowMap& rm, int batch) {
     return 0;
 }
 
+// canonical transforms: rows whose prime qualifies go to the FP64-pipe kernels, the rest to the integer kernels
+static bool split_rows_fp64(const Ctx* c, const RowMap& rm, RowMap& fp, RowMap& rest) {
+    fp.nrows = rest.nrows = 0;
+    if (!fp64_ntt_supported(c)) return false;
+    for (int r = 0; r < rm.nrows; r++) {
+        RowMap& d = c->h_limbs[rm.limb[r]].fp_ok ? fp : rest;
+        d.limb[d.nrows] = rm.limb[r]; d.drow[d.nrows] = rm.drow[r]; d.nrows++;
+    }
+    return fp.nrows > 0;
+}
+
+static int launch_ntt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st);
+static int launch_intt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st);
+
 int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
+    if (check_common(c, rm, batch)) return -1;
+    RowMap fp, rest;
+    if (mode == NTT_CANONICAL && split_rows_fp64(c, rm, fp, rest)) {
+        {
+            ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * fp.nrows * batch, c->logN > 12 ? 2 : 1);
+            if (launch_ntt_fp64(c, fp, false, in, out, batch, st)) return -1;
+        }
+        if (rest.nrows == 0) return 0;
+        return launch_ntt_int(c, rest, in, out, batch, mode, st);
+    }
+    return launch_ntt_int(c, rm, in, out, batch, mode, st);
+}
+
+int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
+    if (check_common(c, rm, batch)) return -1;
+    RowMap fp, rest;
+    if (mode != NTT_REFERENCE_ARITH && split_rows_fp64(c, rm, fp, rest)) {
+        {
+            ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * fp.nrows * batch, c->logN > 12 ? 2 : 1);
+            if (launch_ntt_fp64(c, fp, true, in, out, batch, st)) return -1;
+        }
+        if (rest.nrows == 0) return 0;
+        return launch_intt_int(c, rest, in, out, batch, mode, st);
+    }
+    return launch_intt_int(c, rm, in, out, batch, mode, st);
+}
+
+static int launch_ntt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
     if (check_common(c, rm, batch)) return -1;
     NttParams p;
     p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
@@ -490,7 +538,7 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     return launch_chunk_dyn(cl, false, fast, p, grid, st);
 }
 
-int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
+static int launch_intt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
     // INTTLazy == INTT for N >= 16 (ring/ntt.go:197-206): both are canonical, so both take the fast path;
     // NTT_REFERENCE_ARITH keeps the Montgomery kernels reachable (cross-check in the tests).
     const int fast = (mode != NTT_REFERENCE_ARITH) ? fast_variant(c, rm, true) : 0;

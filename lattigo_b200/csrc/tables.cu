@@ -235,6 +235,17 @@ int upload_limb_tables(Ctx* c, int i) {
     }
     L.fwd_mask = mask;
     L.inv_lazy = ((u128)q << (c->logN + 1)) < ((u128)1 << 64) ? 1u : 0u;
+    // FP64 path
+    L.fp_ok = ((u128)q * (u64)(10 + c->logN) < ((u128)1 << 51)) ? 1u : 0u;
+    L.fq = (double)q; L.fqinv = 1.0 / (double)q;
+    L.fninv = (double)ninv; L.flast_inv = (double)last;
+    double* dft = c->d_ftw + (size_t)(2 * i) * half;
+    L.ftw_fwd = dft; L.ftw_bwd = dft + half;
+    if (L.fp_ok) {
+        std::vector<double> ft(2 * half);
+        for (size_t j = 0; j < half; j++) { ft[j] = (double)tw[2 * j]; ft[half + j] = (double)tw[2 * half + 2 * j]; }
+        LGPU_CUDA_OK(cudaMemcpy(dft, ft.data(), ft.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -322,6 +333,7 @@ int build_context(Ctx* c, int device, int logN, int ring_type, const u64* q, int
     const size_t half = (size_t)(c->nthroot >> 1);
     LGPU_CUDA_OK(cudaMalloc(&c->d_roots, 2 * (size_t)nl * half * sizeof(u64)));
     LGPU_CUDA_OK(cudaMalloc(&c->d_tw, 4 * (size_t)nl * half * sizeof(u64)));
+    LGPU_CUDA_OK(cudaMalloc(&c->d_ftw, 2 * (size_t)nl * half * sizeof(double)));
     c->h_limbs.resize(nl);
     for (int i = 0; i < nl; i++) {
         if (upload_limb_tables(c, i)) return -1;
@@ -346,6 +358,7 @@ void destroy_context(Ctx* c) {
     cudaFree(c->d_limbs);
     cudaFree(c->d_roots);
     cudaFree(c->d_tw);
+    cudaFree(c->d_ftw);
 }
 
 }  // namespace lgpu
