@@ -372,6 +372,18 @@ int decompose_single_ntt(const Ctx* c, int levelQ, int levelP, int nbPi, int dig
 static int gadget_product_multiple_p_lazy(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st) {
     const int levelP = evk.levelP;
     const size_t N = c->N, nq = levelQ + 1, np = levelP + 1;
+    // fused pipeline (keyswitch_fused.cu) when the accumulators are QP-stacked blocks with uniform strides
+    if (ks_fused_applicable(c, levelQ, evk) && cx.row_stride == N && acc.q[0].row_stride == N && acc.p[0].row_stride == N &&
+        acc.p[0].p == acc.q[0].p + nq * N && acc.p[1].p == acc.q[1].p + nq * N && acc.q[1].p > acc.q[0].p &&
+        acc.q[0].batch_stride == acc.q[1].batch_stride && acc.p[0].batch_stride == acc.q[0].batch_stride &&
+        acc.p[1].batch_stride == acc.q[0].batch_stride) {
+        Scratch inv;
+        if (inv.alloc((size_t)batch * nq * N, st)) return -1;
+        Span cxInv{inv.p, N, nq * N};
+        if (launch_intt(c, rows_range(0, 0, (int)nq), cx, cxInv, batch, NTT_CANONICAL, st)) return -1;
+        return gadget_product_multiple_p_fused(c, levelQ, cx, CSpan{inv.p, N, nq * N}, evk, acc.q[0].p, (size_t)(acc.q[1].p - acc.q[0].p),
+                                               acc.q[0].batch_stride, batch, st);
+    }
     Scratch buf;
     if (buf.alloc((size_t)batch * (nq + nq + np) * N, st)) return -1;
     Span cxInv{buf.p, N, nq * N};

@@ -41,6 +41,11 @@ int gadget_product_hoisted(const Ctx* c, int levelQ, const u64* decomp, const Ga
 int evaluator_automorphism(const Ctx* c, int level, CSpan in0, CSpan in1, u64 galEl, const GadgetCt& gk, Span out0, Span out1,
                            const u64* decomp_hoisted, int batch, cudaStream_t st);
 int evaluator_relinearize(const Ctx* c, int level, CSpan c0, CSpan c1, CSpan c2, const GadgetCt& rlk, Span out0, Span out1, int batch, cudaStream_t st);
+// keyswitch_fused.cu
+bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk);
+int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cxInv, const GadgetCt& evk, u64* acc, size_t acc_cs, size_t acc_bs,
+                                    int batch, cudaStream_t st);
+
 int ckks_mulrelin_rescale(const Ctx* c, int level, const u64* ctA, const u64* ctB, const GadgetCt& rlk, int nb_rescales, u64* out, int batch,
                           cudaStream_t st);
 

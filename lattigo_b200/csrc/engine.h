@@ -63,6 +63,7 @@ struct HostSubRing {
 struct ModUpSet {
     int nS = 0, nT = 0;
     size_t off_qoverqiinvqi = 0, off_qoverqimodp = 0, off_vtimesqmodp = 0;
+    size_t off_half_s = 0, off_half_t = 0;  // floor(S/2) mod s_i (nS words) and mod t_j (nT words), S = prod(sources)
 };
 
 struct Ctx {

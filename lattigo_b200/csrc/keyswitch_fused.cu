@@ -1,0 +1,405 @@
+// keyswitch_fused.cu -- fused pipeline for gadgetProductMultiplePLazy (core/rlwe/evaluator_gadget_product.go:129-201),
+// the dominant loop of every key-switch (relinearisation, rotations):
+//
+//     for each digit d:  DecomposeSingleNTT(d) -> MulCoeffsMontgomeryLazy[ThenAddLazy](evk[d], .) on Q and P
+//
+// Unfused this is, per digit and per ciphertext, a basis-extension pass (write l+k rows), a two-pass NTT (read/write
+// them twice) and a MAC pass that reads them again and read-modify-writes 2(l+k) accumulator rows. Here:
+//
+//   K1 ks_prepare   once per ciphertext: y_i = MRed(x_i + half_i, (S/s_i)^-1) for every row and the float64 overflow
+//                   count v of every digit (ring/basis_extension.go:504-548) -- the only part of the basis extension
+//                   that is shared by all target limbs.
+//   K2 ks_strided   one launch for all (digit, target limb): the per-target sum  sum_i y_i (S/s_i mod t) - v S - S/2
+//                   is evaluated on the INTEGER pipes for the 16 coefficients a thread owns and fed straight into
+//                   the first 4 NTT stages (FP64 pipe for primes < 2^46, Shoup integer butterflies otherwise); the
+//                   extended polynomial never exists in memory.
+//   K3 ks_chunk_mac one CTA per (ciphertext, limb, 4096-chunk) walks over ALL digits: remaining 12 NTT stages in
+//                   shared memory, then the Montgomery MAC against evk[d] with the two accumulators resident in
+//                   shared memory; each accumulator row is written once, canonical, instead of 2 x digits times.
+//
+// Only canonical values leave the pipeline (the accumulators after the reference's trailing Reduce are canonical,
+// :179-200), so the arithmetic inside is free-form -- except the float64 `v`, which is computed exactly as the
+// reference does, and the single-limb digit rule (:402-436), which is reproduced literally.
+#include <cstring>
+#include "../../include/lattigo_b200.h"
+#include "composite.h"
+#include "modarith.cuh"
+#include "ntt_arith.cuh"
+
+namespace lgpu {
+
+constexpr int kMaxDigits = 32;
+
+// ------------------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------------------
+struct KsPrepParams {
+    const LimbConst* limbs;
+    const u64* cx; size_t cx_rs, cx_bs;
+    u64* Y; size_t y_bs;
+    unsigned char* V; size_t v_bs;
+    int nq, nd, k, n;
+    u64 half_src[64];
+    u64 cinv[64];
+};
+__global__ void __launch_bounds__(256) ks_prepare_kernel(KsPrepParams p) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.n) return;
+    const int b = blockIdx.y;
+    const u64* src = p.cx + (size_t)b * p.cx_bs + x;
+    u64* Y = p.Y + (size_t)b * p.y_bs + x;
+    unsigned char* V = p.V + (size_t)b * p.v_bs + x;
+    for (int d = 0; d < p.nd; d++) {
+        const int r0 = d * p.k;
+        const int r1 = min(r0 + p.k, p.nq);
+        if (r1 - r0 == 1) {            // single-limb digit: the raw coefficient is consumed by K2 (:402-436)
+            Y[(size_t)r0 * p.n] = src[(size_t)r0 * p.cx_rs];
+            V[(size_t)d * p.n] = 0;
+            continue;
+        }
+        double vi = 0.0;
+        for (int i = r0; i < r1; i++) {
+            const LimbConst& L = p.limbs[i];
+            const u64 yi = mred(src[(size_t)i * p.cx_rs] + p.half_src[i], p.cinv[i], L.q, L.qinv);
+            Y[(size_t)i * p.n] = yi;
+            vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(yi), __ull2double_rn(L.q)));
+        }
+        V[(size_t)d * p.n] = (unsigned char)__double2ull_rz(vi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------------------------
+struct KsDigit {
+    unsigned int off_c, off_vt, off_half_t;   // blob offsets (words) of qoverqimodp / vtimesqmodp / half_t for this digit
+    unsigned short ldc, nS;
+};
+struct KsStridedParams {
+    const LimbConst* limbs;
+    const u64* blob;
+    RowMap rm;                      // launch row -> (global limb, row in the QP-stacked buffers)
+    const u64* Y; size_t y_bs;
+    const unsigned char* V; size_t v_bs;
+    u64* P1; size_t p1_ds, p1_bs;   // [batch][digit][nq+np][N]
+    int logN, nq, k, nd;
+    KsDigit dg[kMaxDigits];
+};
+
+// ext value of one coefficient for target limb (q, qinv): reference formula of multSum + centring, reduced to < 3q.
+template <int NSMAX>
+__device__ __forceinline__ u64 ks_ext(const u64 (&y)[NSMAX], int nS, int v, const u64* c, const u64* vt, u64 half_t, u64 q, u64 qinv) {
+    u64 rhi = 0, rlo = 0;
+#pragma unroll
+    for (int i = 0; i < NSMAX; i++) {
+        if (i < nS) {
+            u64 mhi, mlo;
+            mul128(y[i], c[i], mhi, mlo);
+            rlo += mlo;
+            rhi += mhi + (rlo < mlo);
+        }
+    }
+    const u64 hhi = mulhi64(rlo * qinv, q);
+    u64 r = rhi - hhi + q + vt[v];
+    return cred(r + q - half_t, q);
+}
+
+template <int RL, int NSMAX, bool FP>
+__global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
+    constexpr int R = 1 << RL;
+    __shared__ u64 s_c[NSMAX];
+    __shared__ u64 s_vt[NSMAX + 1];
+    const int limb = p.rm.limb[blockIdx.y];
+    const int row = p.rm.drow[blockIdx.y];
+    const int d = blockIdx.z % p.nd, b = blockIdx.z / p.nd;
+    const KsDigit dg = p.dg[d];
+    const int r0 = d * p.k;
+    const int nS = dg.nS;
+    if (row < p.nq && row >= r0 && row < r0 + nS) return;   // the digit's own rows are taken from the NTT input
+    const LimbConst L = p.limbs[limb];
+    if (threadIdx.x < nS) s_c[threadIdx.x] = p.blob[dg.off_c + (size_t)limb * dg.ldc + threadIdx.x];
+    if (threadIdx.x <= nS) s_vt[threadIdx.x] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + threadIdx.x];
+    __syncthreads();
+    const int N = 1 << p.logN;
+    const int stride = N >> RL;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= stride) return;
+    const u64 q = L.q, qinv = L.qinv;
+    const u64 half_t = nS > 1 ? p.blob[dg.off_half_t + limb] : 0;
+    const u64* Y = p.Y + (size_t)b * p.y_bs + (size_t)r0 * N;
+    const unsigned char* V = p.V + (size_t)b * p.v_bs + (size_t)d * N;
+    u64* out = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N;
+    u64 e[R];
+    if (nS > 1) {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const int x = k * stride + l;
+            u64 y[NSMAX];
+#pragma unroll
+            for (int i = 0; i < NSMAX; i++) y[i] = i < nS ? Y[(size_t)i * N + x] : 0;
+            e[k] = ks_ext<NSMAX>(y, nS, (int)V[x], s_c, s_vt, half_t, q, qinv);
+        }
+    } else {
+        // single-limb digit (ring/basis_extension.go:402-436): centre around q_src/2, reduce, restore the sign
+        const u64 qs = p.limbs[r0].q;
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            u64 c = Y[k * stride + l];
+            const bool neg = c >= (qs >> 1);
+            if (neg) c = qs - c;
+            const u64 t = bred_add(c, q, L.bred_hi);
+            e[k] = neg ? q - t : t;
+        }
+    }
+    if constexpr (FP) {
+        const double fq = L.fq, fqinv = L.fqinv;
+        const double* tw = L.ftw_fwd;
+        double x[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) x[k] = u2d(e[k]);
+#pragma unroll
+        for (int u = 0; u < RL; u++) {
+            const int half = 1 << (RL - 1 - u);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                fp_fwd_bfly(x[k], x[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), fq, fqinv);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) out[(size_t)k * stride + l] = (u64)__double_as_longlong(x[k]);
+    } else {
+        const ulonglong2* tw = L.tw_fwd;
+        const u64 nq = 0ull - q, twoq = q << 1;
+#pragma unroll
+        for (int u = 0; u < RL; u++) {
+            const int half = 1 << (RL - 1 - u);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                fast_fwd_bfly(e[k], e[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), nq, twoq, 0, false);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) out[(size_t)k * stride + l] = e[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------------------
+struct KsChunkParams {
+    const LimbConst* limbs;
+    RowMap rm;
+    const u64* P1; size_t p1_ds, p1_bs;
+    const u64* cx; size_t cx_rs, cx_bs;     // NTT-domain input (the digit's own rows)
+    const u64* evk; size_t evk_ds, evk_cs;  // digit stride, component stride (words); row r of the key at r_key * N
+    int nQk;                                // Q rows in the key
+    u64* acc; size_t acc_cs, acc_bs;        // [batch][2][nq+np][N]
+    int logN, nq, k, nd;
+};
+
+template <bool FP>
+__global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
+    constexpr int CL = 12, T = 256;
+    extern __shared__ u64 smem[];
+    u64* sm = smem;                         // (4096 + 256 + 1) words: transform buffer (padded)
+    u64* a0 = smem + 4096 + 256 + 8;        // 4096 words
+    u64* a1 = a0 + 4096;
+    const int b = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+    const int limb = p.rm.limb[blockIdx.z];
+    const int row = p.rm.drow[blockIdx.z];
+    const LimbConst L = p.limbs[limb];
+    const int s1 = p.logN - CL;
+    const int N = 1 << p.logN;
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
+    const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
+    for (int d = 0; d < p.nd; d++) {
+        const int r0 = d * p.k;
+        const int r1 = min(r0 + p.k, p.nq);
+        const bool own = row < p.nq && row >= r0 && row < r1;
+        const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow;
+        const u64* e1 = e0 + p.evk_cs;
+        if (!own) {
+            const u64* src = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N + ((size_t)chunk << CL);
+            if constexpr (FP) {
+                double* fsm = reinterpret_cast<double*>(sm);
+                fp_fwd_round<CL, 0, 4, 2>(fsm, src, L, s1, chunk, tid);
+                double t2[15];
+                fp_load_tw<CL, 4, 4>(t2, L.ftw_fwd, s1, chunk, tid);
+                __syncthreads();
+                fp_fwd_round_tw<CL, 4, 4>(fsm, t2, L.fq, L.fqinv, tid);
+                double t3[15];
+                fp_load_tw<CL, 8, 4>(t3, L.ftw_fwd, s1, chunk, tid);
+                __syncthreads();
+                fp_fwd_round_tw<CL, 8, 4>(fsm, t3, L.fq, L.fqinv, tid);
+            } else {
+                fwd_round<CL, 0, 4, true, 2>(sm, src, L, s1, p.logN, chunk, tid);
+                __syncthreads();
+                fwd_round<CL, 4, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+                __syncthreads();
+                fwd_round<CL, 8, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+            }
+            __syncthreads();
+        }
+        const u64* xin = p.cx + (size_t)b * p.cx_bs + (size_t)row * p.cx_rs + ((size_t)chunk << CL);
+#pragma unroll 4
+        for (int kk = 0; kk < 16; kk++) {
+            const int idx = kk * T + tid;
+            u64 x;
+            if (own) x = xin[idx];
+            else if (FP) x = fp_canon(reinterpret_cast<double*>(sm)[fpad(idx)], L.fq, L.fqinv);
+            else x = sm[pad_idx(idx)];
+            const u64 m0 = mred_lazy(__ldg(e0 + idx), x, q, qinv);
+            const u64 m1 = mred_lazy(__ldg(e1 + idx), x, q, qinv);
+            if (d == 0) { a0[idx] = m0; a1[idx] = m1; }
+            else {
+                u64 v0 = a0[idx] + m0, v1 = a1[idx] + m1;
+                a0[idx] = v0 >= twoq ? v0 - twoq : v0;
+                a1[idx] = v1 >= twoq ? v1 - twoq : v1;
+            }
+        }
+        __syncthreads();
+    }
+    u64* o0 = p.acc + (size_t)b * p.acc_bs + (size_t)row * N + ((size_t)chunk << CL);
+    u64* o1 = o0 + p.acc_cs;
+#pragma unroll 4
+    for (int kk = 0; kk < 16; kk++) {
+        const int idx = kk * T + tid;
+        const u64 v0 = a0[idx], v1 = a1[idx];
+        o0[idx] = cred(v0 >= twoq ? v0 - twoq : v0, q);
+        o1[idx] = cred(v1 >= twoq ? v1 - twoq : v1, q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------------------------
+bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
+    static const int off = [] { const char* e = getenv("LGPU_NO_FUSED_KS"); return e && atoi(e) ? 1 : 0; }();
+    if (off || c->ring_type != 0) return false;
+    if (c->logN < 13 || c->logN > 17) return false;            // two-pass transforms with a 4096-element chunk pass
+    if (evk.levelP < 1 || evk.pw2 != 0) return false;          // multiple-P path only
+    const int k = evk.levelP + 1;
+    const int nd = base_rns_decomposition_vector_size(levelQ, evk.levelP);
+    if (levelQ + 1 > 64 || nd > kMaxDigits || k > 8) return false;
+    for (int i = 0; i <= levelQ; i++) if (!c->h_limbs[i].fp_ok && c->h_limbs[i].fwd_mask != 0) return false;
+    for (int j = 0; j <= evk.levelP; j++) if (!c->h_limbs[c->nQ + j].fp_ok && c->h_limbs[c->nQ + j].fwd_mask != 0) return false;
+    return true;
+}
+
+template <bool FP>
+static int ks_launch_strided(int rl, int nsmax, const KsStridedParams& p, dim3 grid, cudaStream_t st) {
+#define KS_CASE(RLV) \
+    case RLV: if (nsmax <= 4) ks_strided_kernel<RLV, 4, FP><<<grid, 256, 0, st>>>(p); else ks_strided_kernel<RLV, 8, FP><<<grid, 256, 0, st>>>(p); break;
+    switch (rl) {
+        KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5)
+        default: set_error("unsupported strided radix"); return -1;
+    }
+#undef KS_CASE
+    LGPU_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// acc: QP-stacked accumulators (component c, batch b at acc + c*acc_cs + b*acc_bs, rows 0..nq-1 Q then P; canonical).
+// cx: NTT-domain input, cxInv: its INTT (coefficient domain).
+int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cxInv, const GadgetCt& evk, u64* acc, size_t acc_cs, size_t acc_bs,
+                                    int batch, cudaStream_t st) {
+    const int levelP = evk.levelP;
+    const int k = levelP + 1, nq = levelQ + 1, np = levelP + 1, nrows = nq + np;
+    const int nd = base_rns_decomposition_vector_size(levelQ, levelP);
+    const size_t N = c->N;
+    const int s1 = c->logN - 12;
+    // scratch: Y [batch][nq][N] | P1 [batch][nd][nrows][N] | V [batch][nd][N] bytes
+    const size_t y_words = (size_t)batch * nq * N;
+    const size_t p1_words = (size_t)batch * nd * nrows * N;
+    const size_t v_words = ((size_t)batch * nd * N + 7) / 8;
+    u64* buf = nullptr;
+    LGPU_CUDA_OK(cudaMallocAsync((void**)&buf, (y_words + p1_words + v_words) * sizeof(u64), st));
+    struct Free { u64* p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); } } guard{buf, st};
+    u64* Y = buf;
+    u64* P1 = buf + y_words;
+    unsigned char* V = reinterpret_cast<unsigned char*>(P1 + p1_words);
+
+    // ---- K1
+    KsPrepParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.limbs = c->d_limbs; pp.cx = cxInv.p; pp.cx_rs = cxInv.row_stride; pp.cx_bs = cxInv.batch_stride;
+    pp.Y = Y; pp.y_bs = (size_t)nq * N; pp.V = V; pp.v_bs = (size_t)nd * N;
+    pp.nq = nq; pp.nd = nd; pp.k = k; pp.n = c->N;
+    KsStridedParams sp;
+    memset(&sp, 0, sizeof(sp));
+    int nsmax = 1;
+    for (int d = 0; d < nd; d++) {
+        const int r0 = d * k, r1 = std::min(r0 + k, nq), nS = r1 - r0;
+        sp.dg[d].nS = (unsigned short)nS;
+        if (nS > nsmax) nsmax = nS;
+        if (nS == 1) continue;
+        if (k - 2 >= (int)c->muc_dec.size() || d >= (int)c->muc_dec[k - 2].size() || nS - 2 >= (int)c->muc_dec[k - 2][d].size()) {
+            set_error("no decomposer constants for this (nbPi, digit, level)");
+            return -1;
+        }
+        const ModUpSet& m = c->muc_dec[k - 2][d][nS - 2];
+        for (int i = 0; i < nS; i++) {
+            pp.half_src[r0 + i] = c->h_blob[m.off_half_s + i];
+            pp.cinv[r0 + i] = c->h_blob[m.off_qoverqiinvqi + i];
+        }
+        sp.dg[d].off_c = (unsigned)m.off_qoverqimodp; sp.dg[d].off_vt = (unsigned)m.off_vtimesqmodp;
+        sp.dg[d].off_half_t = (unsigned)m.off_half_t; sp.dg[d].ldc = (unsigned short)m.nS;
+    }
+    {
+        ProfScope ps(LGPU_KCLASS_MODUP, st, 8.0 * N * batch * (2.0 * nq), 1);
+        dim3 grid((unsigned)((N + 255) / 256), batch);
+        ks_prepare_kernel<<<grid, 256, 0, st>>>(pp);
+        LGPU_CUDA_OK(cudaGetLastError());
+    }
+    // row classes
+    RowMap fp, in;
+    fp.nrows = in.nrows = 0;
+    for (int r = 0; r < nrows; r++) {
+        const int limb = r < nq ? r : c->nQ + (r - nq);
+        RowMap& dst = (c->h_limbs[limb].fp_ok && fp64_ntt_supported(c)) ? fp : in;
+        dst.limb[dst.nrows] = (unsigned char)limb; dst.drow[dst.nrows] = (unsigned char)r; dst.nrows++;
+    }
+    // ---- K2
+    sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.Y = Y; sp.y_bs = (size_t)nq * N; sp.V = V; sp.v_bs = (size_t)nd * N;
+    sp.P1 = P1; sp.p1_ds = (size_t)nrows * N; sp.p1_bs = (size_t)nd * nrows * N;
+    sp.logN = c->logN; sp.nq = nq; sp.k = k; sp.nd = nd;
+    {
+        const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
+        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * batch * nd * (double)(nrows - k), (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
+        if (fp.nrows) { sp.rm = fp; if (ks_launch_strided<true>(s1, nsmax, sp, dim3(gx, fp.nrows, nd * batch), st)) return -1; }
+        if (in.nrows) { sp.rm = in; if (ks_launch_strided<false>(s1, nsmax, sp, dim3(gx, in.nrows, nd * batch), st)) return -1; }
+    }
+    // ---- K3
+    KsChunkParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.limbs = c->d_limbs; cp.P1 = P1; cp.p1_ds = sp.p1_ds; cp.p1_bs = sp.p1_bs;
+    cp.cx = cx.p; cp.cx_rs = cx.row_stride; cp.cx_bs = cx.batch_stride;
+    const size_t key_rows = (size_t)(evk.levelQ + 1) + (size_t)(evk.levelP + 1);
+    cp.evk = evk.data; cp.evk_cs = key_rows * N; cp.evk_ds = (size_t)evk.npw2max * 2 * key_rows * N; cp.nQk = evk.levelQ + 1;
+    cp.acc = acc; cp.acc_cs = acc_cs; cp.acc_bs = acc_bs;
+    cp.logN = c->logN; cp.nq = nq; cp.k = k; cp.nd = nd;
+    const size_t smem = (size_t)(4096 + 256 + 8 + 2 * 4096) * sizeof(u64);
+    {
+        // algorithmic bytes: P1 read once + accumulators written once + evk once per launch + own rows
+        ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * (batch * (double)(nd * (nrows - k) + 2 * nrows + nq) + 2.0 * nd * nrows),
+                     (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
+        const unsigned chunks = (unsigned)(N >> 12);
+        if (fp.nrows) {
+            cp.rm = fp;
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_kernel<true><<<dim3(batch, chunks, fp.nrows), 256, smem, st>>>(cp);
+            LGPU_CUDA_OK(cudaGetLastError());
+        }
+        if (in.nrows) {
+            cp.rm = in;
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_kernel<false><<<dim3(batch, chunks, in.nrows), 256, smem, st>>>(cp);
+            LGPU_CUDA_OK(cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
+}  // namespace lgpu

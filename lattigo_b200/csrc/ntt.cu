@@ -26,6 +26,7 @@
 #include "../../include/lattigo_b200.h"
 #include "engine.h"
 #include "modarith.cuh"
+#include "ntt_arith.cuh"
 
 namespace lgpu {
 
@@ -39,56 +40,6 @@ struct NttParams {
     int mode;     // NttMode
     int ci;       // conjugate-invariant ring (stage numbering differs) -- not handled by these kernels
 };
-
-// reference schedule for the forward U >= 4q correction, ring/ntt.go:275-310 (never on stage 0),
-// :318 (bits.Len64(m) odd <=> stage index even), :500-518 (always on the last stage).
-__device__ __forceinline__ bool fwd_reduce_flag(int s, int logN) { return (s == logN - 1) || (s > 0 && (s & 1) == 0); }
-
-__device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qinv, bool reduce) {
-    u64 U = X;
-    u64 fourq = q << 2;
-    if (reduce) U = (U >= fourq) ? U - fourq : U;
-    u64 V = mred_lazy(Y, psi, q, qinv);
-    X = U + V;
-    Y = U + (q << 1) - V;
-}
-// invbutterfly, ring/ntt.go:164-171
-__device__ __forceinline__ void inv_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qinv) {
-    u64 U = X, V = Y;
-    u64 twoq = q << 1;
-    u64 s = U + V;
-    X = (s >= twoq) ? s - twoq : s;
-    Y = mred_lazy(U + (q << 2) - V, psi, q, qinv);
-}
-
-// ---- FAST path primitives ---------------------------------------------------------------------------
-// x*w mod q in [0, 2q) for any x < 2^64, given wp = floor(w * 2^64 / q)
-__device__ __forceinline__ u64 shoup_mul(u64 x, ulonglong2 w, u64 q) { return x * w.x - __umul64hi(x, w.y) * q; }
-
-// CT butterfly: X = U + V*w, Y = U - V*w + 2q (lazy). nq = -q mod 2^64. The sum U + V*w - hi*q is accumulated in
-// the multiplier's addend so that no separate 64-bit additions are issued for X.
-__device__ __forceinline__ void fast_fwd_bfly(u64& X, u64& Y, ulonglong2 w, u64 nq, u64 twoq, u64 kq, bool corr) {
-    u64 U = X;
-    if (corr) U = (U >= kq) ? U - kq : U;
-    const u64 V = Y;
-    const u64 hi = __umul64hi(V, w.y);
-    const u32 v0 = (u32)V, v1 = (u32)(V >> 32), w0 = (u32)w.x, w1 = (u32)(w.x >> 32);
-    const u32 h0 = (u32)hi, h1 = (u32)(hi >> 32), n0 = (u32)nq, n1 = (u32)(nq >> 32);
-    u64 acc = U + (u64)v0 * w0;
-    acc += (u64)h0 * n0;
-    const u32 t = v0 * w1 + v1 * w0 + h0 * n1 + h1 * n0;
-    acc += (u64)t << 32;
-    X = acc;
-    Y = (U << 1) + twoq - acc;
-}
-// GS butterfly: X = U + V (optionally corrected to [0, 2q)), Y = (U - V + addq) * w in [0, 2q)
-__device__ __forceinline__ void fast_inv_bfly(u64& X, u64& Y, ulonglong2 w, u64 q, u64 addq, bool corr) {
-    const u64 U = X, V = Y;
-    u64 s = U + V;
-    if (corr) { const u64 twoq = q << 1; s = (s >= twoq) ? s - twoq : s; }
-    X = s;
-    Y = shoup_mul(U - V + addq, w, q);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // strided pass: global stages [0, RL). Thread l handles elements {k * (N >> RL) + l}.
@@ -187,72 +138,6 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
 // ---------------------------------------------------------------------------------------------------
 // chunk pass: global stages [s1, logN) on a contiguous chunk of C = 2^CL elements held in shared memory.
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int round_bits(int cl, int i) {
-    // radix schedule (bits per register round) for a chunk of 2^cl elements
-    return cl == 12 ? 4
-         : cl == 11 ? (i < 2 ? 4 : 3)
-         : cl == 10 ? (i < 1 ? 4 : 3)
-         : cl == 9  ? 3
-         : cl == 8  ? (i < 2 ? 4 : 0)
-         : cl == 7  ? (i == 0 ? 4 : (i == 1 ? 3 : 0))
-         : cl == 6  ? (i < 2 ? 3 : 0)
-         : cl == 5  ? (i == 0 ? 3 : (i == 1 ? 2 : 0))
-         :            (i == 0 ? 4 : 0);
-}
-__host__ __device__ constexpr int num_rounds(int cl) { return cl >= 9 ? 3 : (cl >= 5 ? 2 : 1); }
-
-__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
-
-// One register round of the forward transform on chunk-local stages [A, A+RB).
-template <int CL, int A, int RB, bool FROM_GLOBAL, int FAST>
-__device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const LimbConst& L,
-                                          int s1, int logN, int chunk, int tid) {
-    const u64 q = L.q, qinv = L.qinv;
-    const u64* roots = L.roots_fwd;
-    const ulonglong2* twp = L.tw_fwd;
-    const u64 nq = 0ull - q, twoq = q << 1;
-    constexpr int G = 16 >> RB;          // groups per thread
-    constexpr int RR = 1 << RB;          // elements per group
-    constexpr int LOB = CL - A - RB;     // bits of `lo`
-#pragma unroll
-    for (int gi = 0; gi < G; gi++) {
-        const int g = tid * G + gi;
-        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
-        const int base = (hi << (CL - A)) + lo;
-        u64 x[RR];
-#pragma unroll
-        for (int k = 0; k < RR; k++) {
-            const int idx = base + (k << LOB);
-            x[k] = FROM_GLOBAL ? gsrc[idx] : sm[pad_idx(idx)];
-        }
-#pragma unroll
-        for (int u = 0; u < RB; u++) {
-            const int half = 1 << (RB - 1 - u);
-            const int s = s1 + A + u;
-            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
-            if constexpr (FAST) {
-                const bool corr = (FAST == 1) && ((L.fwd_mask >> s) & 1u);
-#pragma unroll
-                for (int k = 0; k < RR; k++) {
-                    if (k & half) continue;
-                    const ulonglong2 w = __ldg(twp + twbase + (k >> (RB - u)));
-                    fast_fwd_bfly(x[k], x[k + half], w, nq, twoq, L.kq, corr);
-                }
-            } else {
-                const bool red = fwd_reduce_flag(s, logN);
-#pragma unroll
-                for (int k = 0; k < RR; k++) {
-                    if (k & half) continue;
-                    u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
-                    fwd_bfly(x[k], x[k + half], tw, q, qinv, red);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < RR; k++) sm[pad_idx(base + (k << LOB))] = x[k];
-    }
-}
-
 // One register round of the inverse transform (GS) on chunk-local stages [A, A+RB), processed deepest first.
 template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE, int FAST>
 __device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const LimbConst& L,

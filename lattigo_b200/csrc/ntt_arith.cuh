@@ -1,0 +1,249 @@
+// ntt_arith.cuh -- butterfly arithmetic shared by the transform kernels (ntt.cu, ntt_fp64.cu) and the fused
+// key-switch kernels (keyswitch_fused.cu): the integer-pipe Shoup path and the FP64-pipe path.
+#pragma once
+#include "modarith.cuh"
+
+namespace lgpu {
+
+// ---- FAST path primitives ---------------------------------------------------------------------------
+// x*w mod q in [0, 2q) for any x < 2^64, given wp = floor(w * 2^64 / q)
+__device__ __forceinline__ u64 shoup_mul(u64 x, ulonglong2 w, u64 q) { return x * w.x - __umul64hi(x, w.y) * q; }
+
+// CT butterfly: X = U + V*w, Y = U - V*w + 2q (lazy). nq = -q mod 2^64. The sum U + V*w - hi*q is accumulated in
+// the multiplier's addend so that no separate 64-bit additions are issued for X.
+__device__ __forceinline__ void fast_fwd_bfly(u64& X, u64& Y, ulonglong2 w, u64 nq, u64 twoq, u64 kq, bool corr) {
+    u64 U = X;
+    if (corr) U = (U >= kq) ? U - kq : U;
+    const u64 V = Y;
+    const u64 hi = __umul64hi(V, w.y);
+    const u32 v0 = (u32)V, v1 = (u32)(V >> 32), w0 = (u32)w.x, w1 = (u32)(w.x >> 32);
+    const u32 h0 = (u32)hi, h1 = (u32)(hi >> 32), n0 = (u32)nq, n1 = (u32)(nq >> 32);
+    u64 acc = U + (u64)v0 * w0;
+    acc += (u64)h0 * n0;
+    const u32 t = v0 * w1 + v1 * w0 + h0 * n1 + h1 * n0;
+    acc += (u64)t << 32;
+    X = acc;
+    Y = (U << 1) + twoq - acc;
+}
+// GS butterfly: X = U + V (optionally corrected to [0, 2q)), Y = (U - V + addq) * w in [0, 2q)
+__device__ __forceinline__ void fast_inv_bfly(u64& X, u64& Y, ulonglong2 w, u64 q, u64 addq, bool corr) {
+    const u64 U = X, V = Y;
+    u64 s = U + V;
+    if (corr) { const u64 twoq = q << 1; s = (s >= twoq) ? s - twoq : s; }
+    X = s;
+    Y = shoup_mul(U - V + addq, w, q);
+}
+
+
+// ---- FP64-pipe primitives (primes below 2^46, see ntt_fp64.cu) ----------------------------------------
+#define FP_MAGIC 6755399441055744.0   /* 1.5 * 2^52 */
+#define FP_TWO52 4503599627370496.0   /* 2^52 */
+
+__device__ __forceinline__ double u2d(u64 x) { return __longlong_as_double((long long)(x | 0x4330000000000000ull)) - FP_TWO52; }
+// integer-valued 0 <= d < 2^52
+__device__ __forceinline__ u64 d2u(double d) { return (u64)__double_as_longlong(d + FP_TWO52) & 0x000FFFFFFFFFFFFFull; }
+
+__device__ __forceinline__ double fp_mulmod(double v, double w, double q, double qinv) {
+    const double h = __dmul_rn(v, w);
+    const double l = __fma_rn(v, w, -h);
+    const double t = __dadd_rn(__fma_rn(h, qinv, FP_MAGIC), -FP_MAGIC);
+    const double r = __fma_rn(-t, q, h);
+    return __dadd_rn(r, l);
+}
+// x mod q into (-0.66q, 0.66q)
+__device__ __forceinline__ double fp_reduce(double x, double q, double qinv) {
+    const double t = __dadd_rn(__fma_rn(x, qinv, FP_MAGIC), -FP_MAGIC);
+    return __fma_rn(-t, q, x);
+}
+__device__ __forceinline__ u64 fp_canon(double x, double q, double qinv) {
+    double r = fp_reduce(x, q, qinv);
+    r = r < 0.0 ? r + q : r;
+    return d2u(r);
+}
+__device__ __forceinline__ void fp_fwd_bfly(double& X, double& Y, double w, double q, double qinv) {
+    const double v = fp_mulmod(Y, w, q, qinv);
+    const double u = X;
+    X = __dadd_rn(u, v);
+    Y = __dadd_rn(u, -v);
+}
+__device__ __forceinline__ void fp_inv_bfly(double& X, double& Y, double w, double q, double qinv) {
+    const double u = X, v = Y;
+    X = __dadd_rn(u, v);
+    Y = fp_mulmod(__dadd_rn(u, -v), w, q, qinv);
+}
+
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+
+
+
+// ---- reference (Montgomery) butterflies and the chunk-round machinery ------------------------------------
+// reference schedule for the forward U >= 4q correction, ring/ntt.go:275-310 (never on stage 0),
+// :318 (bits.Len64(m) odd <=> stage index even), :500-518 (always on the last stage).
+__device__ __forceinline__ bool fwd_reduce_flag(int s, int logN) { return (s == logN - 1) || (s > 0 && (s & 1) == 0); }
+
+__device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qinv, bool reduce) {
+    u64 U = X;
+    u64 fourq = q << 2;
+    if (reduce) U = (U >= fourq) ? U - fourq : U;
+    u64 V = mred_lazy(Y, psi, q, qinv);
+    X = U + V;
+    Y = U + (q << 1) - V;
+}
+// invbutterfly, ring/ntt.go:164-171
+__device__ __forceinline__ void inv_bfly(u64& X, u64& Y, u64 psi, u64 q, u64 qinv) {
+    u64 U = X, V = Y;
+    u64 twoq = q << 1;
+    u64 s = U + V;
+    X = (s >= twoq) ? s - twoq : s;
+    Y = mred_lazy(U + (q << 2) - V, psi, q, qinv);
+}
+
+__host__ __device__ constexpr int round_bits(int cl, int i) {
+    // radix schedule (bits per register round) for a chunk of 2^cl elements
+    return cl == 12 ? 4
+         : cl == 11 ? (i < 2 ? 4 : 3)
+         : cl == 10 ? (i < 1 ? 4 : 3)
+         : cl == 9  ? 3
+         : cl == 8  ? (i < 2 ? 4 : 0)
+         : cl == 7  ? (i == 0 ? 4 : (i == 1 ? 3 : 0))
+         : cl == 6  ? (i < 2 ? 3 : 0)
+         : cl == 5  ? (i == 0 ? 3 : (i == 1 ? 2 : 0))
+         :            (i == 0 ? 4 : 0);
+}
+__host__ __device__ constexpr int num_rounds(int cl) { return cl >= 9 ? 3 : (cl >= 5 ? 2 : 1); }
+
+__device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
+
+// One register round of the forward transform on chunk-local stages [A, A+RB).
+template <int CL, int A, int RB, bool FROM_GLOBAL, int FAST>
+__device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const LimbConst& L,
+                                          int s1, int logN, int chunk, int tid) {
+    const u64 q = L.q, qinv = L.qinv;
+    const u64* roots = L.roots_fwd;
+    const ulonglong2* twp = L.tw_fwd;
+    const u64 nq = 0ull - q, twoq = q << 1;
+    constexpr int G = 16 >> RB;          // groups per thread
+    constexpr int RR = 1 << RB;          // elements per group
+    constexpr int LOB = CL - A - RB;     // bits of `lo`
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int g = tid * G + gi;
+        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
+        const int base = (hi << (CL - A)) + lo;
+        u64 x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) {
+            const int idx = base + (k << LOB);
+            x[k] = FROM_GLOBAL ? gsrc[idx] : sm[pad_idx(idx)];
+        }
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int half = 1 << (RB - 1 - u);
+            const int s = s1 + A + u;
+            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+            if constexpr (FAST) {
+                const bool corr = (FAST == 1) && ((L.fwd_mask >> s) & 1u);
+#pragma unroll
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    const ulonglong2 w = __ldg(twp + twbase + (k >> (RB - u)));
+                    fast_fwd_bfly(x[k], x[k + half], w, nq, twoq, L.kq, corr);
+                }
+            } else {
+                const bool red = fwd_reduce_flag(s, logN);
+#pragma unroll
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
+                    fwd_bfly(x[k], x[k + half], tw, q, qinv, red);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k++) sm[pad_idx(base + (k << LOB))] = x[k];
+    }
+}
+
+
+// ---- FP64 chunk rounds ---------------------------------------------------------------------------------
+__host__ __device__ constexpr int fp_round_bits(int cl, int i) {
+    return cl == 12 ? 4 : cl == 11 ? (i < 2 ? 4 : 3) : cl == 10 ? (i < 1 ? 4 : 3) : 0;
+}
+
+template <int CL, int A, int RB, int SRC /*0 smem, 1 global u64, 2 global raw double*/>
+__device__ __forceinline__ void fp_fwd_round(double* sm, const u64* gsrc, const LimbConst& L, int s1, int chunk, int tid) {
+    constexpr int G = 16 >> RB, RR = 1 << RB, LOB = CL - A - RB;
+    const double q = L.fq, qinv = L.fqinv;
+    const double* tw = L.ftw_fwd;
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int g = tid * G + gi;
+        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
+        const int base = (hi << (CL - A)) + lo;
+        double x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) {
+            const int idx = base + (k << LOB);
+            if (SRC == 1) x[k] = u2d(gsrc[idx]);
+            else if (SRC == 2) x[k] = __longlong_as_double((long long)gsrc[idx]);
+            else x[k] = sm[fpad(idx)];
+        }
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int half = 1 << (RB - 1 - u);
+            const int s = s1 + A + u;
+            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+#pragma unroll
+            for (int k = 0; k < RR; k++) {
+                if (k & half) continue;
+                fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (RB - u))), q, qinv);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k++) sm[fpad(base + (k << LOB))] = x[k];
+    }
+}
+
+// Twiddles of one forward round for this thread: G groups x (2^RB - 1) values, loaded BEFORE the barrier that
+// precedes the round so that their L2 latency overlaps the barrier wait instead of following it.
+template <int CL, int A, int RB>
+__device__ __forceinline__ void fp_load_tw(double (&t)[15], const double* tw, int s1, int chunk, int tid) {
+    constexpr int G = 16 >> RB, RR = 1 << RB, LOB = CL - A - RB;
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int hi = (tid * G + gi) >> LOB;
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int twbase = (1 << (s1 + A + u)) + (chunk << (A + u)) + (hi << u);
+#pragma unroll
+            for (int m = 0; m < (1 << u); m++) t[gi * (RR - 1) + (1 << u) - 1 + m] = __ldg(tw + twbase + m);
+        }
+    }
+}
+template <int CL, int A, int RB>
+__device__ __forceinline__ void fp_fwd_round_tw(double* sm, const double (&t)[15], double q, double qinv, int tid) {
+    constexpr int G = 16 >> RB, RR = 1 << RB, LOB = CL - A - RB;
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int g = tid * G + gi;
+        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
+        const int base = (hi << (CL - A)) + lo;
+        double x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) x[k] = sm[fpad(base + (k << LOB))];
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int half = 1 << (RB - 1 - u);
+#pragma unroll
+            for (int k = 0; k < RR; k++) {
+                if (k & half) continue;
+                fp_fwd_bfly(x[k], x[k + half], t[gi * (RR - 1) + (1 << u) - 1 + (k >> (RB - u))], q, qinv);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k++) sm[fpad(base + (k << LOB))] = x[k];
+    }
+}
+
+
+}  // namespace lgpu

@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include "../../include/lattigo_b200.h"
 #include "engine.h"
+#include "modarith.cuh"
+#include "ntt_arith.cuh"
 
 namespace lgpu {
 
@@ -25,44 +27,6 @@ struct FpParams {
     size_t in_rs, in_bs, out_rs, out_bs;
     int logN;
 };
-
-#define FP_MAGIC 6755399441055744.0   /* 1.5 * 2^52 */
-#define FP_TWO52 4503599627370496.0   /* 2^52 */
-
-__device__ __forceinline__ double u2d(u64 x) { return __longlong_as_double((long long)(x | 0x4330000000000000ull)) - FP_TWO52; }
-// integer-valued 0 <= d < 2^52
-__device__ __forceinline__ u64 d2u(double d) { return (u64)__double_as_longlong(d + FP_TWO52) & 0x000FFFFFFFFFFFFFull; }
-
-__device__ __forceinline__ double fp_mulmod(double v, double w, double q, double qinv) {
-    const double h = __dmul_rn(v, w);
-    const double l = __fma_rn(v, w, -h);
-    const double t = __dadd_rn(__fma_rn(h, qinv, FP_MAGIC), -FP_MAGIC);
-    const double r = __fma_rn(-t, q, h);
-    return __dadd_rn(r, l);
-}
-// x mod q into (-0.66q, 0.66q)
-__device__ __forceinline__ double fp_reduce(double x, double q, double qinv) {
-    const double t = __dadd_rn(__fma_rn(x, qinv, FP_MAGIC), -FP_MAGIC);
-    return __fma_rn(-t, q, x);
-}
-__device__ __forceinline__ u64 fp_canon(double x, double q, double qinv) {
-    double r = fp_reduce(x, q, qinv);
-    r = r < 0.0 ? r + q : r;
-    return d2u(r);
-}
-__device__ __forceinline__ void fp_fwd_bfly(double& X, double& Y, double w, double q, double qinv) {
-    const double v = fp_mulmod(Y, w, q, qinv);
-    const double u = X;
-    X = __dadd_rn(u, v);
-    Y = __dadd_rn(u, -v);
-}
-__device__ __forceinline__ void fp_inv_bfly(double& X, double& Y, double w, double q, double qinv) {
-    const double u = X, v = Y;
-    X = __dadd_rn(u, v);
-    Y = fp_mulmod(__dadd_rn(u, -v), w, q, qinv);
-}
-
-__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
 
 // ---- strided pass ------------------------------------------------------------------------------------------
 template <int RL, bool INVERSE>
@@ -123,40 +87,6 @@ __global__ void __launch_bounds__(256) ntt_fp_strided_kernel(FpParams p) {
 }
 
 // ---- chunk pass ------------------------------------------------------------------------------------------
-template <int CL, int A, int RB, int SRC /*0 smem, 1 global u64, 2 global raw double*/>
-__device__ __forceinline__ void fp_fwd_round(double* sm, const u64* gsrc, const LimbConst& L, int s1, int chunk, int tid) {
-    constexpr int G = 16 >> RB, RR = 1 << RB, LOB = CL - A - RB;
-    const double q = L.fq, qinv = L.fqinv;
-    const double* tw = L.ftw_fwd;
-#pragma unroll
-    for (int gi = 0; gi < G; gi++) {
-        const int g = tid * G + gi;
-        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
-        const int base = (hi << (CL - A)) + lo;
-        double x[RR];
-#pragma unroll
-        for (int k = 0; k < RR; k++) {
-            const int idx = base + (k << LOB);
-            if (SRC == 1) x[k] = u2d(gsrc[idx]);
-            else if (SRC == 2) x[k] = __longlong_as_double((long long)gsrc[idx]);
-            else x[k] = sm[fpad(idx)];
-        }
-#pragma unroll
-        for (int u = 0; u < RB; u++) {
-            const int half = 1 << (RB - 1 - u);
-            const int s = s1 + A + u;
-            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
-#pragma unroll
-            for (int k = 0; k < RR; k++) {
-                if (k & half) continue;
-                fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (RB - u))), q, qinv);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < RR; k++) sm[fpad(base + (k << LOB))] = x[k];
-    }
-}
-
 // inverse round over chunk-local stages [A, A+RB), deepest first; inputs |x| < 0.66q; DST: 0 smem (renormalised),
 // 1 global raw doubles (renormalised), 2 global canonical u64 with N^-1 folded into the last stage (single pass)
 template <int CL, int A, int RB, int DST>
@@ -206,42 +136,79 @@ __device__ __forceinline__ void fp_inv_round(double* sm, u64* gdst, const LimbCo
     }
 }
 
-__host__ __device__ constexpr int fp_round_bits(int cl, int i) {
-    return cl == 12 ? 4 : cl == 11 ? (i < 2 ? 4 : 3) : cl == 10 ? (i < 1 ? 4 : 3) : 0;
-}
-
+// Forward chunk pass. One CTA owns a (limb, chunk) pair and walks over `bpc` batch elements: the twiddles of that
+// pair stay in L1, and the next element's 16 values per thread are prefetched into registers while the current
+// element is in its second and third rounds, so the round-one global-load latency is hidden.
 template <int CL>
-__global__ void __launch_bounds__((1 << CL) / 16, 2) ntt_fp_chunk_fwd_kernel(FpParams p) {
+__global__ void __launch_bounds__((1 << CL) / 16, 2) ntt_fp_chunk_fwd_kernel(FpParams p, int batch, int bpc) {
     constexpr int T = (1 << CL) / 16;
     constexpr int R0 = fp_round_bits(CL, 0), R1 = fp_round_bits(CL, 1), R2 = fp_round_bits(CL, 2);
+    static_assert(R0 == 4, "first round is radix-16");
     extern __shared__ double fsm[];
-    const int b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
+    const int chunk = blockIdx.x, tid = threadIdx.x;
     const LimbConst L = p.limbs[p.rm.limb[blockIdx.y]];
     const int row = p.rm.drow[blockIdx.y];
     const int s1 = p.logN - CL;
-    const u64* src = (s1 > 0 ? (const u64*)p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs
-                             : p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs) + ((size_t)chunk << CL);
-    u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
+    const int b0 = blockIdx.z * bpc;
+    const int b1 = min(b0 + bpc, batch);
+    const double q = L.fq, qinv = L.fqinv;
+    const double* tw = L.ftw_fwd;
     {   // pull the last round's twiddle lines (8 B x 15 per thread) into L1 early
-        const double* tw = L.ftw_fwd;
 #pragma unroll
         for (int u = 0; u < R2; u++) {
             const int s = s1 + R0 + R1 + u;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(tw + (1 << s) + (chunk << (R0 + R1 + u)) + (tid << u)));
         }
     }
-    if (s1 > 0) fp_fwd_round<CL, 0, R0, 2>(fsm, src, L, s1, chunk, tid);
-    else        fp_fwd_round<CL, 0, R0, 1>(fsm, src, L, s1, chunk, tid);
-    __syncthreads();
-    fp_fwd_round<CL, R0, R1, 0>(fsm, nullptr, L, s1, chunk, tid);
-    __syncthreads();
-    fp_fwd_round<CL, R0 + R1, R2, 0>(fsm, nullptr, L, s1, chunk, tid);
-    __syncthreads();
-    const double q = L.fq, qinv = L.fqinv;
+    auto src_of = [&](int b) {
+        return (s1 > 0 ? (const u64*)p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs
+                       : p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs) + ((size_t)chunk << CL);
+    };
+    u64 raw[16];
+    {
+        const u64* src = src_of(b0);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int idx = k * T + tid;
-        dst[idx] = fp_canon(fsm[fpad(idx)], q, qinv);
+        for (int k = 0; k < 16; k++) raw[k] = src[k * T + tid];
+    }
+    for (int b = b0; b < b1; b++) {
+        u64* dst = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs + ((size_t)chunk << CL);
+        {   // round 1 from registers: element k of this thread sits at k*T + tid (hi = 0, lo = tid)
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = (s1 > 0) ? __longlong_as_double((long long)raw[k]) : u2d(raw[k]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int half = 1 << (3 - u);
+                const int twbase = (1 << (s1 + u)) + (chunk << u);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k & half) continue;
+                    fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (4 - u))), q, qinv);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) fsm[fpad(k * T + tid)] = x[k];
+        }
+        double t2[15];
+        fp_load_tw<CL, R0, R1>(t2, tw, s1, chunk, tid);
+        __syncthreads();
+        if (b + 1 < b1) {   // prefetch the next element while rounds 2 and 3 run
+            const u64* src = src_of(b + 1);
+#pragma unroll
+            for (int k = 0; k < 16; k++) raw[k] = src[k * T + tid];
+        }
+        fp_fwd_round_tw<CL, R0, R1>(fsm, t2, q, qinv, tid);
+        double t3[15];
+        fp_load_tw<CL, R0 + R1, R2>(t3, tw, s1, chunk, tid);
+        __syncthreads();
+        fp_fwd_round_tw<CL, R0 + R1, R2>(fsm, t3, q, qinv, tid);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int idx = k * T + tid;
+            dst[idx] = fp_canon(fsm[fpad(idx)], q, qinv);
+        }
+        __syncthreads();
     }
 }
 
@@ -273,12 +240,26 @@ __global__ void __launch_bounds__((1 << CL) / 16, 2) ntt_fp_chunk_inv_kernel(FpP
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------
+// batch elements per CTA of the forward chunk pass: as many as possible while keeping >= ~4 waves of CTAs
+static int fp_batch_per_cta(int chunks, int rows, int batch) {
+    static const int forced = [] { const char* e = getenv("LGPU_NTT_BPC"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return forced < batch ? forced : batch;
+    int bpc = batch;
+    while (bpc > 1 && (long)chunks * rows * ((batch + bpc - 1) / bpc) < 4L * 296) bpc = (bpc + 1) / 2;
+    return bpc;
+}
+
 template <int CL>
 static int fp_launch_chunk(bool inverse, const FpParams& p, dim3 grid, cudaStream_t st) {
     constexpr int C = 1 << CL;
     const size_t smem = (size_t)(C + (C >> 4) + 1) * sizeof(double);
     if (inverse) ntt_fp_chunk_inv_kernel<CL><<<grid, C / 16, smem, st>>>(p);
-    else         ntt_fp_chunk_fwd_kernel<CL><<<grid, C / 16, smem, st>>>(p);
+    else {
+        const int batch = grid.z;
+        const int bpc = fp_batch_per_cta(grid.x, grid.y, batch);
+        dim3 g2(grid.x, grid.y, (batch + bpc - 1) / bpc);
+        ntt_fp_chunk_fwd_kernel<CL><<<g2, C / 16, smem, st>>>(p, batch, bpc);
+    }
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
 }

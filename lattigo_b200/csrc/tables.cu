@@ -178,6 +178,10 @@ static ModUpSet gen_modup(std::vector<u64>& blob, const u64* S, int nS, const u6
             blob.push_back(acc);
         }
     }
+    m.off_half_s = blob.size();
+    for (int i = 0; i < nS; i++) blob.push_back(h_half_prod_mod(S, nS, S[i]));
+    m.off_half_t = blob.size();
+    for (int j = 0; j < nT; j++) blob.push_back(h_half_prod_mod(S, nS, T[j]));
     return m;
 }
 

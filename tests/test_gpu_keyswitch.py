@@ -233,6 +233,18 @@ def test_gadget_product_multiple_p():
     _gadget_case(lb, 8, H.Qi60[:5], H.Pi60[:2], 0, (4, 2), seed=2)
 
 
+def test_gadget_product_fused_pipeline_logn13():
+    """logN = 13 is the smallest ring that takes the fused key-switch pipeline (keyswitch_fused.cu): FP64 rows (45-bit
+    primes) and integer rows (55/56-bit) mixed, ragged last digit, single-limb last digit, k = 3 and k = 2."""
+    lb = _lb()
+    q, p = _mods(13, [56, 45, 45, 45, 45, 45, 45], [55, 55, 55])
+    _gadget_case(lb, 13, q, p, 0, (6, 5, 4, 3, 2, 0), seed=11)
+    _gadget_case(lb, 13, q, p[:2], 0, (6, 5, 1), seed=12)
+    # 40-bit scale primes, 50-bit P (examples/params.go:115-120 shape)
+    q, p = _mods(14, [51, 40, 40, 40, 40], [50, 50])
+    _gadget_case(lb, 14, q, p, 0, (4, 3), batch=3, seed=13)
+
+
 def test_gadget_product_single_p_and_bit_decomp():
     """core/rlwe/test_params.go:28-49: k = 1 with pw2 = 16; k = 0 (no P) with pw2 = 2; k = 1 without pw2."""
     lb = _lb()
