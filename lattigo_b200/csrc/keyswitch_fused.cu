@@ -39,6 +39,8 @@ struct KsPrepParams {
     u64* Y; size_t y_bs;
     unsigned char* V; size_t v_bs;
     int nq, nd, k, n;
+    int limb0;        // global limb index of source row 0 (0 for Q sources, nQ for P sources)
+    int single_rule;  // 1: one-limb digits follow Decomposer's rule (raw coefficient, :402-436); 0: always ModUpExact
     u64 half_src[64];
     u64 cinv[64];
 };
@@ -52,14 +54,14 @@ __global__ void __launch_bounds__(256) ks_prepare_kernel(KsPrepParams p) {
     for (int d = 0; d < p.nd; d++) {
         const int r0 = d * p.k;
         const int r1 = min(r0 + p.k, p.nq);
-        if (r1 - r0 == 1) {            // single-limb digit: the raw coefficient is consumed by K2 (:402-436)
+        if (r1 - r0 == 1 && p.single_rule) {   // single-limb digit: the raw coefficient is consumed by K2 (:402-436)
             Y[(size_t)r0 * p.n] = src[(size_t)r0 * p.cx_rs];
             V[(size_t)d * p.n] = 0;
             continue;
         }
         double vi = 0.0;
         for (int i = r0; i < r1; i++) {
-            const LimbConst& L = p.limbs[i];
+            const LimbConst& L = p.limbs[p.limb0 + i];
             const u64 yi = mred(src[(size_t)i * p.cx_rs] + p.half_src[i], p.cinv[i], L.q, L.qinv);
             Y[(size_t)i * p.n] = yi;
             vi = __dadd_rn(vi, __ddiv_rn(__ull2double_rn(yi), __ull2double_rn(L.q)));
@@ -83,6 +85,12 @@ struct KsStridedParams {
     const unsigned char* V; size_t v_bs;
     u64* P1; size_t p1_ds, p1_bs;   // [batch][digit][nq+np][N]
     int logN, nq, k, nd;
+    int skip_own;     // 1: rows that belong to the digit itself are skipped (key-switch); 0: every launch row is a target
+    int single_rule;  // see KsPrepParams
+    int src_limb0;    // global limb of source row 0 (single-limb rule only)
+    // PRO_BCAST (rescale): e = cred(bc[x] + bc_add, bc_q) + s0[launch row]
+    const u64* bc; size_t bc_bs; u64 bc_add, bc_q;
+    u64 s0[kMaxRows];
     KsDigit dg[kMaxDigits];
 };
 
@@ -104,7 +112,9 @@ __device__ __forceinline__ u64 ks_ext(const u64 (&y)[NSMAX], int nS, int v, cons
     return cred(r + q - half_t, q);
 }
 
-template <int RL, int NSMAX, bool FP>
+enum { PRO_MODUP = 0, PRO_BCAST = 1 };
+
+template <int RL, int NSMAX, bool FP, int PRO>
 __global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
     constexpr int R = 1 << RL;
     __shared__ u64 s_c[NSMAX];
@@ -115,22 +125,31 @@ __global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
     const KsDigit dg = p.dg[d];
     const int r0 = d * p.k;
     const int nS = dg.nS;
-    if (row < p.nq && row >= r0 && row < r0 + nS) return;   // the digit's own rows are taken from the NTT input
+    if (PRO == PRO_MODUP && p.skip_own && row < p.nq && row >= r0 && row < r0 + nS) return;   // own rows come from the NTT input
     const LimbConst L = p.limbs[limb];
-    if (threadIdx.x < nS) s_c[threadIdx.x] = p.blob[dg.off_c + (size_t)limb * dg.ldc + threadIdx.x];
-    if (threadIdx.x <= nS) s_vt[threadIdx.x] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + threadIdx.x];
+    if (PRO == PRO_MODUP) {
+        if (threadIdx.x < nS) s_c[threadIdx.x] = p.blob[dg.off_c + (size_t)limb * dg.ldc + threadIdx.x];
+        if (threadIdx.x <= nS) s_vt[threadIdx.x] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + threadIdx.x];
+    }
     __syncthreads();
     const int N = 1 << p.logN;
     const int stride = N >> RL;
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= stride) return;
     const u64 q = L.q, qinv = L.qinv;
-    const u64 half_t = nS > 1 ? p.blob[dg.off_half_t + limb] : 0;
-    const u64* Y = p.Y + (size_t)b * p.y_bs + (size_t)r0 * N;
-    const unsigned char* V = p.V + (size_t)b * p.v_bs + (size_t)d * N;
     u64* out = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N;
     u64 e[R];
-    if (nS > 1) {
+    if constexpr (PRO == PRO_BCAST) {
+        const u64* bc = p.bc + (size_t)b * p.bc_bs;
+        const u64 s0 = p.s0[blockIdx.y];
+#pragma unroll
+        for (int k = 0; k < R; k++) e[k] = cred(bc[k * stride + l] + p.bc_add, p.bc_q) + s0;
+    } else {
+    const bool multi = nS > 1 || !p.single_rule;
+    const u64 half_t = multi ? p.blob[dg.off_half_t + limb] : 0;
+    const u64* Y = p.Y + (size_t)b * p.y_bs + (size_t)r0 * N;
+    const unsigned char* V = p.V + (size_t)b * p.v_bs + (size_t)d * N;
+    if (multi) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
             const int x = k * stride + l;
@@ -141,7 +160,7 @@ __global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
         }
     } else {
         // single-limb digit (ring/basis_extension.go:402-436): centre around q_src/2, reduce, restore the sign
-        const u64 qs = p.limbs[r0].q;
+        const u64 qs = p.limbs[p.src_limb0 + r0].q;
 #pragma unroll
         for (int k = 0; k < R; k++) {
             u64 c = Y[k * stride + l];
@@ -150,6 +169,7 @@ __global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
             const u64 t = bred_add(c, q, L.bred_hi);
             e[k] = neg ? q - t : t;
         }
+    }
     }
     if constexpr (FP) {
         const double fq = L.fq, fqinv = L.fqinv;
@@ -288,10 +308,10 @@ bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
     return true;
 }
 
-template <bool FP>
+template <bool FP, int PRO = PRO_MODUP>
 static int ks_launch_strided(int rl, int nsmax, const KsStridedParams& p, dim3 grid, cudaStream_t st) {
 #define KS_CASE(RLV) \
-    case RLV: if (nsmax <= 4) ks_strided_kernel<RLV, 4, FP><<<grid, 256, 0, st>>>(p); else ks_strided_kernel<RLV, 8, FP><<<grid, 256, 0, st>>>(p); break;
+    case RLV: if (nsmax <= 4) ks_strided_kernel<RLV, 4, FP, PRO><<<grid, 256, 0, st>>>(p); else ks_strided_kernel<RLV, 8, FP, PRO><<<grid, 256, 0, st>>>(p); break;
     switch (rl) {
         KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5)
         default: set_error("unsupported strided radix"); return -1;
@@ -326,7 +346,7 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
     memset(&pp, 0, sizeof(pp));
     pp.limbs = c->d_limbs; pp.cx = cxInv.p; pp.cx_rs = cxInv.row_stride; pp.cx_bs = cxInv.batch_stride;
     pp.Y = Y; pp.y_bs = (size_t)nq * N; pp.V = V; pp.v_bs = (size_t)nd * N;
-    pp.nq = nq; pp.nd = nd; pp.k = k; pp.n = c->N;
+    pp.nq = nq; pp.nd = nd; pp.k = k; pp.n = c->N; pp.limb0 = 0; pp.single_rule = 1;
     KsStridedParams sp;
     memset(&sp, 0, sizeof(sp));
     int nsmax = 1;
@@ -364,7 +384,7 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
     // ---- K2
     sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.Y = Y; sp.y_bs = (size_t)nq * N; sp.V = V; sp.v_bs = (size_t)nd * N;
     sp.P1 = P1; sp.p1_ds = (size_t)nrows * N; sp.p1_bs = (size_t)nd * nrows * N;
-    sp.logN = c->logN; sp.nq = nq; sp.k = k; sp.nd = nd;
+    sp.logN = c->logN; sp.nq = nq; sp.k = k; sp.nd = nd; sp.skip_own = 1; sp.single_rule = 1; sp.src_limb0 = 0;
     {
         const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
         ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * batch * nd * (double)(nrows - k), (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
@@ -398,6 +418,217 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
             ks_chunk_mac_kernel<false><<<dim3(batch, chunks, in.nrows), 256, smem, st>>>(cp);
             LGPU_CUDA_OK(cudaGetLastError());
         }
+    }
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// chunk pass with an element-wise epilogue: out = CRed( MRed(x + 2q - a, s) [+ d] ), x = NTT(P1 row).
+// Used by the fused ModDown (a = accumulator Q rows, s = -P^-1, d = the other summand of the ciphertext) and the
+// fused rescale (a = input rows, s = RescaleConstants): SubThenMulScalarMontgomeryTwoModulus, ring/vec_ops.go:752.
+// Buffers with a (component, batch) structure are addressed as  z -> (z / nb) * cs + (z % nb) * bs.
+// ------------------------------------------------------------------------------------------------------------
+struct FzChunkParams {
+    const LimbConst* limbs;
+    RowMap rm;
+    const u64* P1; size_t p1_bs;
+    const u64* A; size_t a_cs, a_bs;
+    const u64* D; size_t d_cs, d_bs;
+    u64* out; size_t o_cs, o_bs;
+    int nb, logN;
+    u64 s[kMaxRows];
+};
+
+template <bool FP>
+__global__ void __launch_bounds__(256, 2) fz_chunk_epi_kernel(FzChunkParams p) {
+    constexpr int CL = 12, T = 256;
+    extern __shared__ u64 smem[];
+    u64* sm = smem;
+    const int chunk = blockIdx.x, z = blockIdx.z, tid = threadIdx.x;
+    const int limb = p.rm.limb[blockIdx.y];
+    const int row = p.rm.drow[blockIdx.y];
+    const LimbConst L = p.limbs[limb];
+    const int s1 = p.logN - CL;
+    const int N = 1 << p.logN;
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
+    const u64 sc = p.s[blockIdx.y];
+    const int zc = z / p.nb, zb = z % p.nb;
+    const size_t roff = (size_t)row * N + ((size_t)chunk << CL);
+    const u64* src = p.P1 + (size_t)z * p.p1_bs + roff;
+    const u64* A = p.A + (size_t)zc * p.a_cs + (size_t)zb * p.a_bs + roff;
+    const u64* D = p.D ? p.D + (size_t)zc * p.d_cs + (size_t)zb * p.d_bs + roff : nullptr;
+    u64* out = p.out + (size_t)zc * p.o_cs + (size_t)zb * p.o_bs + roff;
+    if constexpr (FP) {
+        double* fsm = reinterpret_cast<double*>(sm);
+        fp_fwd_round<CL, 0, 4, 2>(fsm, src, L, s1, chunk, tid);
+        double t2[15];
+        fp_load_tw<CL, 4, 4>(t2, L.ftw_fwd, s1, chunk, tid);
+        __syncthreads();
+        fp_fwd_round_tw<CL, 4, 4>(fsm, t2, L.fq, L.fqinv, tid);
+        double t3[15];
+        fp_load_tw<CL, 8, 4>(t3, L.ftw_fwd, s1, chunk, tid);
+        __syncthreads();
+        fp_fwd_round_tw<CL, 8, 4>(fsm, t3, L.fq, L.fqinv, tid);
+    } else {
+        fwd_round<CL, 0, 4, true, 2>(sm, src, L, s1, p.logN, chunk, tid);
+        __syncthreads();
+        fwd_round<CL, 4, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+        __syncthreads();
+        fwd_round<CL, 8, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kk = 0; kk < 16; kk++) {
+        const int idx = kk * T + tid;
+        u64 x;
+        if (FP) x = fp_canon(reinterpret_cast<double*>(sm)[fpad(idx)], L.fq, L.fqinv);
+        else x = sm[pad_idx(idx)];
+        u64 r = mred(x + twoq - A[idx], sc, q, qinv);
+        if (D) r = cred(r + D[idx], q);
+        out[idx] = r;
+    }
+}
+
+template <bool FP>
+static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = (size_t)(4096 + 256 + 8) * sizeof(u64);
+    fz_chunk_epi_kernel<FP><<<grid, 256, smem, st>>>(p);
+    LGPU_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static void split_rows(const Ctx* c, int limb0, int nrows, RowMap& fp, RowMap& in) {
+    fp.nrows = in.nrows = 0;
+    for (int r = 0; r < nrows; r++) {
+        const int limb = limb0 + r;
+        RowMap& dst = (c->h_limbs[limb].fp_ok && fp64_ntt_supported(c)) ? fp : in;
+        dst.limb[dst.nrows] = (unsigned char)limb; dst.drow[dst.nrows] = (unsigned char)r; dst.nrows++;
+    }
+}
+
+bool fz_applicable(const Ctx* c, int levelQ, int levelP) {
+    static const int off = [] { const char* e = getenv("LGPU_NO_FUSED_KS"); return e && atoi(e) ? 1 : 0; }();
+    if (off || c->ring_type != 0 || c->logN < 13 || c->logN > 17) return false;
+    if (levelQ + 1 > kMaxRows || levelP + 1 > 8) return false;
+    for (int i = 0; i <= levelQ; i++) if (!c->h_limbs[i].fp_ok && c->h_limbs[i].fwd_mask != 0) return false;
+    return true;
+}
+
+// Fused Evaluator.ModDown (NTT -> NTT, core/rlwe/evaluator_gadget_product.go:39-52 = 2 x ModDownQPtoQNTT,
+// ring/basis_extension.go:235-256) for ncomp x batch QP-stacked accumulators, with an optional addend:
+//     out[c][b] = (accQ[c][b] - NTT(ModUpPtoQ(INTT(accP[c][b])))) * P^-1  (+ D[c][b])
+int moddown_ntt_fused(const Ctx* c, int levelQ, int levelP, const u64* acc, size_t acc_cs, size_t acc_bs, const u64* D, size_t d_cs, size_t d_bs,
+                      u64* out, size_t o_cs, size_t o_bs, int ncomp, int batch, cudaStream_t st) {
+    const int nq = levelQ + 1, np = levelP + 1;
+    const size_t N = c->N;
+    const int Z = ncomp * batch;
+    const int s1 = c->logN - 12;
+    const size_t bp_words = (size_t)Z * np * N, y_words = bp_words, p1_words = (size_t)Z * nq * N, v_words = ((size_t)Z * N + 7) / 8;
+    u64* buf = nullptr;
+    LGPU_CUDA_OK(cudaMallocAsync((void**)&buf, (bp_words + y_words + p1_words + v_words) * sizeof(u64), st));
+    struct Free { u64* p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); } } guard{buf, st};
+    u64* buffP = buf; u64* Y = buffP + bp_words; u64* P1 = Y + y_words;
+    unsigned char* V = reinterpret_cast<unsigned char*>(P1 + p1_words);
+    // A: INTT of the P rows
+    RowMap rp;
+    rp.nrows = np;
+    for (int j = 0; j < np; j++) { rp.limb[j] = (unsigned char)(c->nQ + j); rp.drow[j] = (unsigned char)j; }
+    for (int cc = 0; cc < ncomp; cc++) {
+        CSpan in{acc + (size_t)cc * acc_cs + (size_t)nq * N, N, acc_bs};
+        Span o{buffP + (size_t)cc * batch * np * N, N, (size_t)np * N};
+        if (launch_intt(c, rp, in, o, batch, NTT_CANONICAL, st)) return -1;
+    }
+    // B: y_i, v
+    const ModUpSet& m = c->muc_PtoQ[levelP];
+    KsPrepParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.limbs = c->d_limbs; pp.cx = buffP; pp.cx_rs = N; pp.cx_bs = (size_t)np * N;
+    pp.Y = Y; pp.y_bs = (size_t)np * N; pp.V = V; pp.v_bs = N;
+    pp.nq = np; pp.nd = 1; pp.k = np; pp.n = c->N; pp.limb0 = c->nQ; pp.single_rule = 0;
+    for (int i = 0; i < np; i++) { pp.half_src[i] = c->h_blob[m.off_half_s + i]; pp.cinv[i] = c->h_blob[m.off_qoverqiinvqi + i]; }
+    {
+        ProfScope ps(LGPU_KCLASS_MODUP, st, 8.0 * N * Z * (2.0 * np), 1);
+        ks_prepare_kernel<<<dim3((unsigned)((N + 255) / 256), Z), 256, 0, st>>>(pp);
+        LGPU_CUDA_OK(cudaGetLastError());
+    }
+    // C: basis extension folded into the strided pass
+    RowMap fp, in;
+    split_rows(c, 0, nq, fp, in);
+    KsStridedParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.Y = Y; sp.y_bs = (size_t)np * N; sp.V = V; sp.v_bs = N;
+    sp.P1 = P1; sp.p1_ds = (size_t)nq * N; sp.p1_bs = (size_t)nq * N;
+    sp.logN = c->logN; sp.nq = nq; sp.k = np; sp.nd = 1; sp.skip_own = 0; sp.single_rule = 0; sp.src_limb0 = c->nQ;
+    sp.dg[0].nS = (unsigned short)np; sp.dg[0].ldc = (unsigned short)m.nS;
+    sp.dg[0].off_c = (unsigned)m.off_qoverqimodp; sp.dg[0].off_vt = (unsigned)m.off_vtimesqmodp; sp.dg[0].off_half_t = (unsigned)m.off_half_t;
+    {
+        const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
+        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * (double)nq, (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
+        if (fp.nrows) { sp.rm = fp; if (ks_launch_strided<true>(s1, np, sp, dim3(gx, fp.nrows, Z), st)) return -1; }
+        if (in.nrows) { sp.rm = in; if (ks_launch_strided<false>(s1, np, sp, dim3(gx, in.nrows, Z), st)) return -1; }
+    }
+    // D: chunk pass + (accQ - x) * (-P^-1) [+ D]
+    FzChunkParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.limbs = c->d_limbs; cp.P1 = P1; cp.p1_bs = (size_t)nq * N;
+    cp.A = acc; cp.a_cs = acc_cs; cp.a_bs = acc_bs; cp.D = D; cp.d_cs = d_cs; cp.d_bs = d_bs;
+    cp.out = out; cp.o_cs = o_cs; cp.o_bs = o_bs; cp.nb = batch; cp.logN = c->logN;
+    {
+        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * nq * (D ? 4.0 : 3.0), (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
+        const unsigned chunks = (unsigned)(N >> 12);
+        auto scal = [&](const RowMap& rm) { for (int r = 0; r < rm.nrows; r++) { const int i = rm.drow[r]; cp.s[r] = c->Q[i] - c->mdc_PtoQ[(size_t)levelP * c->nQ + i]; } };
+        if (fp.nrows) { cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1; }
+        if (in.nrows) { cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), st)) return -1; }
+    }
+    return 0;
+}
+
+// Fused Ring.DivRoundByLastModulusNTT (ring/scaling.go:101-122) for ncomp x batch polynomials at level `level`:
+// X rows 0..level -> out rows 0..level-1.
+int div_round_last_ntt_fused(const Ctx* c, int level, const u64* X, size_t x_cs, size_t x_bs, u64* out, size_t o_cs, size_t o_bs,
+                             int ncomp, int batch, cudaStream_t st) {
+    const size_t N = c->N;
+    const int Z = ncomp * batch;
+    const int s1 = c->logN - 12;
+    u64* buf = nullptr;
+    LGPU_CUDA_OK(cudaMallocAsync((void**)&buf, ((size_t)Z * N + (size_t)Z * level * N) * sizeof(u64), st));
+    struct Free { u64* p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); } } guard{buf, st};
+    u64* r = buf; u64* P1 = buf + (size_t)Z * N;
+    RowMap rl;
+    rl.nrows = 1; rl.limb[0] = (unsigned char)level; rl.drow[0] = 0;
+    for (int cc = 0; cc < ncomp; cc++) {
+        CSpan in{X + (size_t)cc * x_cs + (size_t)level * N, N, x_bs};
+        Span o{r + (size_t)cc * batch * N, N, N};
+        if (launch_intt(c, rl, in, o, batch, NTT_CANONICAL, st)) return -1;
+    }
+    const u64 qL = c->Q[level];
+    const u64 pHalf = (qL - 1) >> 1;
+    RowMap fp, in;
+    split_rows(c, 0, level, fp, in);
+    KsStridedParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.P1 = P1; sp.p1_ds = (size_t)level * N; sp.p1_bs = (size_t)level * N;
+    sp.logN = c->logN; sp.nq = level; sp.k = 1; sp.nd = 1;
+    sp.bc = r; sp.bc_bs = N; sp.bc_add = pHalf; sp.bc_q = qL;
+    {
+        const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
+        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * (double)level, (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
+        auto s0 = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) { const u64 qi = c->Q[rm.drow[k]]; sp.s0[k] = qi - (pHalf % qi); } };
+        if (fp.nrows) { sp.rm = fp; s0(fp); if (ks_launch_strided<true, PRO_BCAST>(s1, 1, sp, dim3(gx, fp.nrows, Z), st)) return -1; }
+        if (in.nrows) { sp.rm = in; s0(in); if (ks_launch_strided<false, PRO_BCAST>(s1, 1, sp, dim3(gx, in.nrows, Z), st)) return -1; }
+    }
+    FzChunkParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.limbs = c->d_limbs; cp.P1 = P1; cp.p1_bs = (size_t)level * N;
+    cp.A = X; cp.a_cs = x_cs; cp.a_bs = x_bs; cp.D = nullptr;
+    cp.out = out; cp.o_cs = o_cs; cp.o_bs = o_bs; cp.nb = batch; cp.logN = c->logN;
+    {
+        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * level * 3.0, (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
+        const unsigned chunks = (unsigned)(N >> 12);
+        auto scal = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) cp.s[k] = c->rescaleQ[(size_t)(level - 1) * c->nQ + rm.drow[k]]; };
+        if (fp.nrows) { cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1; }
+        if (in.nrows) { cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), st)) return -1; }
     }
     return 0;
 }
