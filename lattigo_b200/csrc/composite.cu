@@ -475,6 +475,17 @@ int gadget_product_lazy(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk,
 // Evaluator.ModDown (core/rlwe/evaluator_gadget_product.go:39-97), NTT -> NTT case.
 int evaluator_moddown_ntt(const Ctx* c, int levelQ, int levelP, const AccSpans& acc, Span ct0, Span ct1, int batch, cudaStream_t st) {
     Span out[2] = {ct0, ct1};
+    {
+        const size_t N = c->N, nq = levelQ + 1;
+        if (levelP >= 0 && fz_applicable(c, levelQ, levelP) && acc.q[0].row_stride == N && acc.p[0].row_stride == N &&
+            acc.p[0].p == acc.q[0].p + nq * N && acc.p[1].p == acc.q[1].p + nq * N && acc.q[1].p > acc.q[0].p &&
+            acc.q[0].batch_stride == acc.q[1].batch_stride && acc.p[0].batch_stride == acc.q[0].batch_stride &&
+            acc.p[1].batch_stride == acc.q[0].batch_stride && ct0.row_stride == N && ct1.row_stride == N && ct1.p > ct0.p &&
+            ct0.batch_stride == ct1.batch_stride && ct0.p != acc.q[0].p) {
+            return moddown_ntt_fused(c, levelQ, levelP, acc.q[0].p, (size_t)(acc.q[1].p - acc.q[0].p), acc.q[0].batch_stride, nullptr, 0, 0,
+                                     ct0.p, (size_t)(ct1.p - ct0.p), ct0.batch_stride, 2, batch, st);
+        }
+    }
     for (int k = 0; k < 2; k++) {
         CSpan aq{acc.q[k].p, acc.q[k].row_stride, acc.q[k].batch_stride};
         if (levelP != -1) {
@@ -691,6 +702,30 @@ static int ckks_mulrelin_rescale_chunk(const Ctx* c, int level, const u64* ctA, 
         dim3 grid((c->N / 2 + 255) / 256, (unsigned)nq, batch);
         ckks_tensor_kernel<<<grid, 256, 0, st>>>(p);
         LGPU_CUDA_OK(cudaGetLastError());
+    }
+    if (rlk.levelP >= 1 && rlk.pw2 == 0 && fz_applicable(c, level, rlk.levelP) && (nb_rescales == 0 || (nb_rescales == 1 && level >= 1))) {
+        // fused tail: accumulators -> (ModDown + add of d0/d1) in one chunk-pass epilogue -> fused rescale
+        const size_t np = rlk.levelP + 1;
+        Scratch accb;
+        if (accb.alloc((size_t)2 * batch * (nq + np) * N, st)) return -1;
+        AccSpans acc;
+        for (int k = 0; k < 2; k++) {
+            u64* base = accb.p + (size_t)k * batch * (nq + np) * N;
+            acc.q[k] = Span{base, N, (nq + np) * N};
+            acc.p[k] = Span{base + nq * N, N, (nq + np) * N};
+        }
+        if (gadget_product_lazy(c, level, CSpan{d2, N, nq * N}, rlk, acc, batch, st)) return -1;
+        // d0, d1 are consecutive [comp][batch][nq][N] blocks: out = d + ModDown(acc), in place
+        if (moddown_ntt_fused(c, level, rlk.levelP, accb.p, (size_t)batch * (nq + np) * N, (nq + np) * N, d0, (size_t)batch * nq * N, nq * N,
+                              d0, (size_t)batch * nq * N, nq * N, 2, batch, st)) return -1;
+        if (nb_rescales == 1) {
+            const size_t nqo = nq - 1;
+            return div_round_last_ntt_fused(c, level, d0, (size_t)batch * nq * N, nq * N, out, nqo * N, 2 * nqo * N, 2, batch, st);
+        }
+        for (int k = 0; k < 2; k++)
+            LGPU_CUDA_OK(cudaMemcpy2DAsync(out + (size_t)k * nq * N, ct_stride * 8, d0 + (size_t)k * batch * nq * N, nq * N * 8, nq * N * 8, batch,
+                                           cudaMemcpyDeviceToDevice, st));
+        return 0;
     }
     if (gadget_product(c, level, CSpan{d2, N, nq * N}, rlk, Span{t0, N, nq * N}, Span{t1, N, nq * N}, batch, st)) return -1;
     RowMap rm = rows_range(0, 0, (int)nq);

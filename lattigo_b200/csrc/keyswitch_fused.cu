@@ -234,49 +234,108 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
     const int N = 1 << p.logN;
     const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
     const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
+    const u64* P1row = p.P1 + (size_t)b * p.p1_bs + (size_t)row * N + ((size_t)chunk << CL);
+    const u64* xin = p.cx + (size_t)b * p.cx_bs + (size_t)row * p.cx_rs + ((size_t)chunk << CL);
+    // digits whose limbs contain this row contribute the NTT-domain input itself; at most one such digit exists
+    const int own_d = row < p.nq ? row / p.k : -1;
+    // software pipeline: the tile of the next digit is fetched into registers while the current one is transformed
+    u64 raw[16];
+    {
+        const int d0 = own_d == 0 ? 1 : 0;
+        if (d0 < p.nd) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) raw[k] = P1row[(size_t)d0 * p.p1_ds + k * T + tid];
+        }
+    }
     for (int d = 0; d < p.nd; d++) {
-        const int r0 = d * p.k;
-        const int r1 = min(r0 + p.k, p.nq);
-        const bool own = row < p.nq && row >= r0 && row < r1;
+        const bool own = d == own_d;
         const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow;
         const u64* e1 = e0 + p.evk_cs;
         if (!own) {
-            const u64* src = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N + ((size_t)chunk << CL);
+            int dn = d + 1;
+            if (dn == own_d) dn++;
             if constexpr (FP) {
                 double* fsm = reinterpret_cast<double*>(sm);
-                fp_fwd_round<CL, 0, 4, 2>(fsm, src, L, s1, chunk, tid);
+                const double fq = L.fq, fqinv = L.fqinv;
+                const double* tw = L.ftw_fwd;
+                {
+                    double x[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) x[k] = __longlong_as_double((long long)raw[k]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int half = 1 << (3 - u);
+                        const int twbase = (1 << (s1 + u)) + (chunk << u);
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            if (k & half) continue;
+                            fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (4 - u))), fq, fqinv);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; k++) fsm[fpad(k * T + tid)] = x[k];
+                }
                 double t2[15];
-                fp_load_tw<CL, 4, 4>(t2, L.ftw_fwd, s1, chunk, tid);
+                fp_load_tw<CL, 4, 4>(t2, tw, s1, chunk, tid);
                 __syncthreads();
-                fp_fwd_round_tw<CL, 4, 4>(fsm, t2, L.fq, L.fqinv, tid);
+                if (dn < p.nd) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
+                }
+                fp_fwd_round_tw<CL, 4, 4>(fsm, t2, fq, fqinv, tid);
                 double t3[15];
-                fp_load_tw<CL, 8, 4>(t3, L.ftw_fwd, s1, chunk, tid);
+                fp_load_tw<CL, 8, 4>(t3, tw, s1, chunk, tid);
                 __syncthreads();
-                fp_fwd_round_tw<CL, 8, 4>(fsm, t3, L.fq, L.fqinv, tid);
+                fp_fwd_round_tw<CL, 8, 4>(fsm, t3, fq, fqinv, tid);
             } else {
-                fwd_round<CL, 0, 4, true, 2>(sm, src, L, s1, p.logN, chunk, tid);
+                const ulonglong2* tw = L.tw_fwd;
+                const u64 nq = 0ull - q;
+                {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int half = 1 << (3 - u);
+                        const int twbase = (1 << (s1 + u)) + (chunk << u);
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            if (k & half) continue;
+                            fast_fwd_bfly(raw[k], raw[k + half], __ldg(tw + twbase + (k >> (4 - u))), nq, twoq, 0, false);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; k++) sm[pad_idx(k * T + tid)] = raw[k];
+                }
                 __syncthreads();
+                if (dn < p.nd) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
+                }
                 fwd_round<CL, 4, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
                 __syncthreads();
                 fwd_round<CL, 8, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
             }
             __syncthreads();
         }
-        const u64* xin = p.cx + (size_t)b * p.cx_bs + (size_t)row * p.cx_rs + ((size_t)chunk << CL);
-#pragma unroll 4
-        for (int kk = 0; kk < 16; kk++) {
-            const int idx = kk * T + tid;
-            u64 x;
-            if (own) x = xin[idx];
-            else if (FP) x = fp_canon(reinterpret_cast<double*>(sm)[fpad(idx)], L.fq, L.fqinv);
-            else x = sm[pad_idx(idx)];
-            const u64 m0 = mred_lazy(__ldg(e0 + idx), x, q, qinv);
-            const u64 m1 = mred_lazy(__ldg(e1 + idx), x, q, qinv);
-            if (d == 0) { a0[idx] = m0; a1[idx] = m1; }
-            else {
-                u64 v0 = a0[idx] + m0, v1 = a1[idx] + m1;
-                a0[idx] = v0 >= twoq ? v0 - twoq : v0;
-                a1[idx] = v1 >= twoq ? v1 - twoq : v1;
+        // MAC against evk[d]: the 32 key words of this thread are requested up front (two batches of 8 + 8)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            u64 k0[8], k1[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const int idx = (h * 8 + j) * T + tid; k0[j] = __ldg(e0 + idx); k1[j] = __ldg(e1 + idx); }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = (h * 8 + j) * T + tid;
+                u64 x;
+                if (own) x = xin[idx];
+                else if (FP) x = fp_canon(reinterpret_cast<double*>(sm)[fpad(idx)], L.fq, L.fqinv);
+                else x = sm[pad_idx(idx)];
+                const u64 m0 = mred_lazy(k0[j], x, q, qinv);
+                const u64 m1 = mred_lazy(k1[j], x, q, qinv);
+                if (d == 0) { a0[idx] = m0; a1[idx] = m1; }
+                else {
+                    u64 v0 = a0[idx] + m0, v1 = a1[idx] + m1;
+                    a0[idx] = v0 >= twoq ? v0 - twoq : v0;
+                    a1[idx] = v1 >= twoq ? v1 - twoq : v1;
+                }
             }
         }
         __syncthreads();
