@@ -64,6 +64,7 @@ struct ModUpSet {
     int nS = 0, nT = 0;
     size_t off_qoverqiinvqi = 0, off_qoverqimodp = 0, off_vtimesqmodp = 0;
     size_t off_half_s = 0, off_half_t = 0;  // floor(S/2) mod s_i (nS words) and mod t_j (nT words), S = prod(sources)
+    size_t off_c_plain = 0;                 // (S/s_i mod t_j) NOT in Montgomery form, [nT][nS] (FP64 basis extension)
 };
 
 struct Ctx {

@@ -30,6 +30,40 @@ namespace lgpu {
 
 constexpr int kMaxDigits = 32;
 
+// The integer-pipe rows (primes >= 2^46: q0 and the special primes) and the FP64-pipe rows of one operation are
+// independent chains that use different execution pipes, so they are issued on two streams and overlap on the SMs.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream(int device) {
+    static thread_local SideStream ss[16];
+    static const int off = [] { const char* e = getenv("LGPU_NO_SIDE_STREAM"); return e && atoi(e) ? 1 : 0; }();
+    if (off || device < 0 || device >= 16) return nullptr;
+    SideStream& x = ss[device];
+    if (!x.s) {
+        if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
+    }
+    return &x;
+}
+// returns the stream for the integer chain (forked from `st`), or `st` itself when side streams are unavailable
+static cudaStream_t fork_side(const Ctx* c, cudaStream_t st, bool have_both) {
+    if (!have_both) return st;
+    SideStream* ss = side_stream(c->device);
+    if (!ss) return st;
+    cudaEventRecord(ss->fork, st);
+    cudaStreamWaitEvent(ss->s, ss->fork, 0);
+    return ss->s;
+}
+static void join_side(const Ctx* c, cudaStream_t st, cudaStream_t side) {
+    if (side == st) return;
+    SideStream* ss = side_stream(c->device);
+    cudaEventRecord(ss->join, side);
+    cudaStreamWaitEvent(st, ss->join, 0);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------------------
@@ -75,7 +109,9 @@ __global__ void __launch_bounds__(256) ks_prepare_kernel(KsPrepParams p) {
 // ------------------------------------------------------------------------------------------------------------
 struct KsDigit {
     unsigned int off_c, off_vt, off_half_t;   // blob offsets (words) of qoverqimodp / vtimesqmodp / half_t for this digit
+    unsigned int off_cp;                      // plain (non-Montgomery) qoverqimodp, for the FP64 evaluation
     unsigned short ldc, nS;
+    unsigned short fp_src;                    // 1: every source prime of the digit is below 2^46 (y_i exact in doubles)
 };
 struct KsStridedParams {
     const LimbConst* limbs;
@@ -127,8 +163,9 @@ __global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
     const int nS = dg.nS;
     if (PRO == PRO_MODUP && p.skip_own && row < p.nq && row >= r0 && row < r0 + nS) return;   // own rows come from the NTT input
     const LimbConst L = p.limbs[limb];
+    const bool fpsum = FP && PRO == PRO_MODUP && dg.fp_src && (nS > 1 || !p.single_rule);
     if (PRO == PRO_MODUP) {
-        if (threadIdx.x < nS) s_c[threadIdx.x] = p.blob[dg.off_c + (size_t)limb * dg.ldc + threadIdx.x];
+        if (threadIdx.x < nS) s_c[threadIdx.x] = p.blob[(fpsum ? dg.off_cp : dg.off_c) + (size_t)limb * dg.ldc + threadIdx.x];
         if (threadIdx.x <= nS) s_vt[threadIdx.x] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + threadIdx.x];
     }
     __syncthreads();
@@ -138,6 +175,42 @@ __global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
     if (l >= stride) return;
     const u64 q = L.q, qinv = L.qinv;
     u64* out = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N;
+    if constexpr (FP && PRO == PRO_MODUP) {
+        if (fpsum) {
+            // FP64 evaluation of the basis extension (targets and sources below 2^46): 5 FP64 operations per product
+            // instead of a 128-bit integer MAC; any representative of the value is fine here, v is the exact one from K1.
+            const double fq = L.fq, fqinv = L.fqinv;
+            const double* tw = L.ftw_fwd;
+            const u64* Y = p.Y + (size_t)b * p.y_bs + (size_t)r0 * N;
+            const unsigned char* V = p.V + (size_t)b * p.v_bs + (size_t)d * N;
+            const double halfd = (double)p.blob[dg.off_half_t + limb];
+            double cj[NSMAX];
+#pragma unroll
+            for (int i = 0; i < NSMAX; i++) cj[i] = i < nS ? (double)s_c[i] : 0.0;
+            double x[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                const int xi = k * stride + l;
+                double acc = __dadd_rn((double)s_vt[V[xi]], -halfd);
+#pragma unroll
+                for (int i = 0; i < NSMAX; i++)
+                    if (i < nS) acc = __dadd_rn(acc, fp_mulmod(u2d(Y[(size_t)i * N + xi]), cj[i], fq, fqinv));
+                x[k] = acc;
+            }
+#pragma unroll
+            for (int u = 0; u < RL; u++) {
+                const int half = 1 << (RL - 1 - u);
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    if (k & half) continue;
+                    fp_fwd_bfly(x[k], x[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), fq, fqinv);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < R; k++) out[(size_t)k * stride + l] = (u64)__double_as_longlong(x[k]);
+            return;
+        }
+    }
     u64 e[R];
     if constexpr (PRO == PRO_BCAST) {
         const u64* bc = p.bc + (size_t)b * p.bc_bs;
@@ -425,6 +498,10 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         }
         sp.dg[d].off_c = (unsigned)m.off_qoverqimodp; sp.dg[d].off_vt = (unsigned)m.off_vtimesqmodp;
         sp.dg[d].off_half_t = (unsigned)m.off_half_t; sp.dg[d].ldc = (unsigned short)m.nS;
+        sp.dg[d].off_cp = (unsigned)m.off_c_plain;
+        bool fps = true;
+        for (int i = r0; i < r1; i++) fps = fps && c->h_limbs[i].fp_ok;
+        sp.dg[d].fp_src = fps ? 1 : 0;
     }
     {
         ProfScope ps(LGPU_KCLASS_MODUP, st, 8.0 * N * batch * (2.0 * nq), 1);
@@ -440,17 +517,10 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         RowMap& dst = (c->h_limbs[limb].fp_ok && fp64_ntt_supported(c)) ? fp : in;
         dst.limb[dst.nrows] = (unsigned char)limb; dst.drow[dst.nrows] = (unsigned char)r; dst.nrows++;
     }
-    // ---- K2
+    // ---- K2 + K3: FP64 rows on `st`, integer rows on the side stream
     sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.Y = Y; sp.y_bs = (size_t)nq * N; sp.V = V; sp.v_bs = (size_t)nd * N;
     sp.P1 = P1; sp.p1_ds = (size_t)nrows * N; sp.p1_bs = (size_t)nd * nrows * N;
     sp.logN = c->logN; sp.nq = nq; sp.k = k; sp.nd = nd; sp.skip_own = 1; sp.single_rule = 1; sp.src_limb0 = 0;
-    {
-        const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
-        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * batch * nd * (double)(nrows - k), (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
-        if (fp.nrows) { sp.rm = fp; if (ks_launch_strided<true>(s1, nsmax, sp, dim3(gx, fp.nrows, nd * batch), st)) return -1; }
-        if (in.nrows) { sp.rm = in; if (ks_launch_strided<false>(s1, nsmax, sp, dim3(gx, in.nrows, nd * batch), st)) return -1; }
-    }
-    // ---- K3
     KsChunkParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.limbs = c->d_limbs; cp.P1 = P1; cp.p1_ds = sp.p1_ds; cp.p1_bs = sp.p1_bs;
@@ -460,24 +530,33 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
     cp.acc = acc; cp.acc_cs = acc_cs; cp.acc_bs = acc_bs;
     cp.logN = c->logN; cp.nq = nq; cp.k = k; cp.nd = nd;
     const size_t smem = (size_t)(4096 + 256 + 8 + 2 * 4096) * sizeof(u64);
-    {
-        // algorithmic bytes: P1 read once + accumulators written once + evk once per launch + own rows
-        ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * (batch * (double)(nd * (nrows - k) + 2 * nrows + nq) + 2.0 * nd * nrows),
-                     (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
-        const unsigned chunks = (unsigned)(N >> 12);
-        if (fp.nrows) {
-            cp.rm = fp;
-            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_kernel<true><<<dim3(batch, chunks, fp.nrows), 256, smem, st>>>(cp);
-            LGPU_CUDA_OK(cudaGetLastError());
+    const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
+    const unsigned chunks = (unsigned)(N >> 12);
+    cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
+    if (in.nrows) {
+        sp.rm = in; cp.rm = in;
+        {
+            ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * batch * nd * (double)in.nrows, 1);
+            if (ks_launch_strided<false>(s1, nsmax, sp, dim3(gx, in.nrows, nd * batch), sint)) return -1;
         }
-        if (in.nrows) {
-            cp.rm = in;
-            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_kernel<false><<<dim3(batch, chunks, in.nrows), 256, smem, st>>>(cp);
-            LGPU_CUDA_OK(cudaGetLastError());
-        }
+        ProfScope ps(LGPU_KCLASS_MAC, sint, 8.0 * N * in.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
+        LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ks_chunk_mac_kernel<false><<<dim3(batch, chunks, in.nrows), 256, smem, sint>>>(cp);
+        LGPU_CUDA_OK(cudaGetLastError());
     }
+    if (fp.nrows) {
+        sp.rm = fp; cp.rm = fp;
+        {
+            ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * batch * nd * (double)fp.nrows, 1);
+            if (ks_launch_strided<true>(s1, nsmax, sp, dim3(gx, fp.nrows, nd * batch), st)) return -1;
+        }
+        // algorithmic bytes: P1 read once + accumulators written once + evk once per launch
+        ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * fp.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
+        LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ks_chunk_mac_kernel<true><<<dim3(batch, chunks, fp.nrows), 256, smem, st>>>(cp);
+        LGPU_CUDA_OK(cudaGetLastError());
+    }
+    join_side(c, st, sint);
     return 0;
 }
 
@@ -621,25 +700,32 @@ int moddown_ntt_fused(const Ctx* c, int levelQ, int levelP, const u64* acc, size
     sp.logN = c->logN; sp.nq = nq; sp.k = np; sp.nd = 1; sp.skip_own = 0; sp.single_rule = 0; sp.src_limb0 = c->nQ;
     sp.dg[0].nS = (unsigned short)np; sp.dg[0].ldc = (unsigned short)m.nS;
     sp.dg[0].off_c = (unsigned)m.off_qoverqimodp; sp.dg[0].off_vt = (unsigned)m.off_vtimesqmodp; sp.dg[0].off_half_t = (unsigned)m.off_half_t;
+    sp.dg[0].off_cp = (unsigned)m.off_c_plain;
     {
-        const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
-        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * (double)nq, (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
-        if (fp.nrows) { sp.rm = fp; if (ks_launch_strided<true>(s1, np, sp, dim3(gx, fp.nrows, Z), st)) return -1; }
-        if (in.nrows) { sp.rm = in; if (ks_launch_strided<false>(s1, np, sp, dim3(gx, in.nrows, Z), st)) return -1; }
+        bool fps = true;
+        for (int j = 0; j < np; j++) fps = fps && c->h_limbs[c->nQ + j].fp_ok;
+        sp.dg[0].fp_src = fps ? 1 : 0;
     }
-    // D: chunk pass + (accQ - x) * (-P^-1) [+ D]
     FzChunkParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.limbs = c->d_limbs; cp.P1 = P1; cp.p1_bs = (size_t)nq * N;
     cp.A = acc; cp.a_cs = acc_cs; cp.a_bs = acc_bs; cp.D = D; cp.d_cs = d_cs; cp.d_bs = d_bs;
     cp.out = out; cp.o_cs = o_cs; cp.o_bs = o_bs; cp.nb = batch; cp.logN = c->logN;
-    {
-        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * nq * (D ? 4.0 : 3.0), (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
-        const unsigned chunks = (unsigned)(N >> 12);
-        auto scal = [&](const RowMap& rm) { for (int r = 0; r < rm.nrows; r++) { const int i = rm.drow[r]; cp.s[r] = c->Q[i] - c->mdc_PtoQ[(size_t)levelP * c->nQ + i]; } };
-        if (fp.nrows) { cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1; }
-        if (in.nrows) { cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), st)) return -1; }
+    const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
+    const unsigned chunks = (unsigned)(N >> 12);
+    auto scal = [&](const RowMap& rm) { for (int r = 0; r < rm.nrows; r++) { const int i = rm.drow[r]; cp.s[r] = c->Q[i] - c->mdc_PtoQ[(size_t)levelP * c->nQ + i]; } };
+    cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
+    if (in.nrows) {
+        ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows * (D ? 5.0 : 4.0), 2);
+        sp.rm = in; if (ks_launch_strided<false>(s1, np, sp, dim3(gx, in.nrows, Z), sint)) return -1;
+        cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), sint)) return -1;
     }
+    if (fp.nrows) {
+        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows * (D ? 5.0 : 4.0), 2);
+        sp.rm = fp; if (ks_launch_strided<true>(s1, np, sp, dim3(gx, fp.nrows, Z), st)) return -1;
+        cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1;
+    }
+    join_side(c, st, sint);
     return 0;
 }
 
@@ -670,25 +756,27 @@ int div_round_last_ntt_fused(const Ctx* c, int level, const u64* X, size_t x_cs,
     sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.P1 = P1; sp.p1_ds = (size_t)level * N; sp.p1_bs = (size_t)level * N;
     sp.logN = c->logN; sp.nq = level; sp.k = 1; sp.nd = 1;
     sp.bc = r; sp.bc_bs = N; sp.bc_add = pHalf; sp.bc_q = qL;
-    {
-        const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
-        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * (double)level, (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
-        auto s0 = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) { const u64 qi = c->Q[rm.drow[k]]; sp.s0[k] = qi - (pHalf % qi); } };
-        if (fp.nrows) { sp.rm = fp; s0(fp); if (ks_launch_strided<true, PRO_BCAST>(s1, 1, sp, dim3(gx, fp.nrows, Z), st)) return -1; }
-        if (in.nrows) { sp.rm = in; s0(in); if (ks_launch_strided<false, PRO_BCAST>(s1, 1, sp, dim3(gx, in.nrows, Z), st)) return -1; }
-    }
     FzChunkParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.limbs = c->d_limbs; cp.P1 = P1; cp.p1_bs = (size_t)level * N;
     cp.A = X; cp.a_cs = x_cs; cp.a_bs = x_bs; cp.D = nullptr;
     cp.out = out; cp.o_cs = o_cs; cp.o_bs = o_bs; cp.nb = batch; cp.logN = c->logN;
-    {
-        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * level * 3.0, (fp.nrows ? 1 : 0) + (in.nrows ? 1 : 0));
-        const unsigned chunks = (unsigned)(N >> 12);
-        auto scal = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) cp.s[k] = c->rescaleQ[(size_t)(level - 1) * c->nQ + rm.drow[k]]; };
-        if (fp.nrows) { cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1; }
-        if (in.nrows) { cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), st)) return -1; }
+    const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
+    const unsigned chunks = (unsigned)(N >> 12);
+    auto s0 = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) { const u64 qi = c->Q[rm.drow[k]]; sp.s0[k] = qi - (pHalf % qi); } };
+    auto scal = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) cp.s[k] = c->rescaleQ[(size_t)(level - 1) * c->nQ + rm.drow[k]]; };
+    cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
+    if (in.nrows) {
+        ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows * 4.0, 2);
+        sp.rm = in; s0(in); if (ks_launch_strided<false, PRO_BCAST>(s1, 1, sp, dim3(gx, in.nrows, Z), sint)) return -1;
+        cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), sint)) return -1;
     }
+    if (fp.nrows) {
+        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows * 4.0, 2);
+        sp.rm = fp; s0(fp); if (ks_launch_strided<true, PRO_BCAST>(s1, 1, sp, dim3(gx, fp.nrows, Z), st)) return -1;
+        cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1;
+    }
+    join_side(c, st, sint);
     return 0;
 }
 

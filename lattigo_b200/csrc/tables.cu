@@ -182,6 +182,15 @@ static ModUpSet gen_modup(std::vector<u64>& blob, const u64* S, int nS, const u6
     for (int i = 0; i < nS; i++) blob.push_back(h_half_prod_mod(S, nS, S[i]));
     m.off_half_t = blob.size();
     for (int j = 0; j < nT; j++) blob.push_back(h_half_prod_mod(S, nS, T[j]));
+    m.off_c_plain = blob.size();
+    for (int j = 0; j < nT; j++) {
+        const u64 pj = T[j];
+        for (int i = 0; i < nS; i++) {
+            u64 pr = 1 % pj;
+            for (int u = 0; u < nS; u++) if (u != i) pr = h_mulmod(pr, S[u] % pj, pj);
+            blob.push_back(pr);
+        }
+    }
     return m;
 }
 
@@ -349,6 +358,15 @@ int build_context(Ctx* c, int device, int logN, int ring_type, const u64* q, int
         LGPU_CUDA_OK(cudaMemcpy(c->d_blob, c->h_blob.data(), c->h_blob.size() * sizeof(u64), cudaMemcpyHostToDevice));
     }
     LGPU_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        // scratch comes from the stream-ordered allocator: keep freed blocks cached in the pool instead of returning
+        // them to the driver at every synchronisation (default release threshold is 0)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     return 0;
 }
 
