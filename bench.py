@@ -274,14 +274,50 @@ def gpu_main(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        ntt_ms = ms[0] + ms[1]; ntt_b = by[0] + by[1]
-        ach = (ntt_b / 1e9) / (ntt_ms * 1e-3) if ntt_ms > 0 else 0.0
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
         tot = sum(ms[i] for i in range(nk)) or 1.0
-        roof = {"bound": "hbm", "kernel": "ntt (forward + inverse transforms: strided pass + chunk pass kernels)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": None, "alg_bytes_per_limb_transform": 16 * N, "share_of_step": ntt_ms / tot,
-                "avg_us_per_limb_transform": 1e3 * ntt_ms / max(1.0, ntt_b / (16.0 * N)), "classes": classes}
+        # dominant kernel class of the step (by summed CUDA-event time of its launch scopes)
+        dom = max(range(nk), key=lambda i: ms[i])
+        kernel_names = {
+            "mac": "ks_chunk_mac_kernel (fused: chunk-pass NTT, 12 stages, + key-switch MAC over all digits; accumulators in smem)",
+            "fused": "ks_strided_kernel / fz_chunk_epi_kernel (basis extension folded into the strided NTT pass; ModDown / rescale epilogues)",
+            "ntt_fwd": "ntt strided + chunk pass kernels (forward)", "ntt_inv": "ntt chunk + strided pass kernels (inverse)",
+            "modup": "ks_prepare_kernel / modup_kernel", "vecop": "vecop_kernel", "tensor": "ckks_tensor_kernel",
+            "automorphism": "auto_ntt_kernel"}
+        ach = (by[dom] / 1e9) / (ms[dom] * 1e-3) if ms[dom] > 0 else 0.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            ent = tr.get(names[dom])
+            if ent and ent.get("preset") == args.preset:
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        # standalone transform rate (BASELINE metric "NTT GB/s vs roofline"): Ring.NTT on all Q limbs of the preset,
+        # 8 polynomials per launch (184 MB in + 184 MB out > L2), CUDA events around `iters` launches
+        xs = rand_rows(Q, (8,)); ys = torch.empty_like(xs)
+        rq = ctx.ringQ
+        for _ in range(3):
+            rq.NTT(xs, ys)
+        torch.cuda.synchronize()
+        ea = torch.cuda.Event(enable_timing=True); eb = torch.cuda.Event(enable_timing=True)
+        iters = 20
+        ea.record()
+        for _ in range(iters):
+            rq.NTT(xs, ys)
+        eb.record(); torch.cuda.synchronize()
+        t_ntt = ea.elapsed_time(eb) * 1e-3 / iters
+        ntt_bytes = 16.0 * N * len(Q) * 8
+        ntt_standalone = {"op": "Ring.NTT, %d limbs x 8 polynomials, N=2^%d" % (len(Q), logN), "us_per_launch": t_ntt * 1e6,
+                          "us_per_limb_transform": t_ntt * 1e6 / (len(Q) * 8), "alg_bytes_per_launch": ntt_bytes,
+                          "achieved": ntt_bytes / t_ntt / 1e9, "unit": "GB/s", "frac": ntt_bytes / t_ntt / 1e9 / peak}
+        del xs, ys
+        roof = {"bound": "hbm", "kernel": kernel_names.get(names[dom], names[dom]), "kernel_class": names[dom],
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                "traffic": traffic, "avg_launch_ms": ms[dom] / max(1, int(sc[dom])), "alg_bytes_per_launch": by[dom] / max(1, int(sc[dom])),
+                "share_of_step": ms[dom] / tot, "ntt_standalone": ntt_standalone, "classes": classes,
+                "note": "classes: summed CUDA-event time of launch scopes on their launching streams over the same K steps; "
+                        "integer-row chains run on a side stream concurrently with the FP64-row chains, so class times may overlap"}
     barrier()
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region) ------

@@ -48,6 +48,13 @@ static SideStream* side_stream(int device) {
     }
     return &x;
 }
+// Measured: evaluating the basis extension on the FP64 pipe (fp_src == 2) makes K2 ~25 % slower than the 128-bit integer
+// MAC, because the FP64 pipe then carries both the extension and the butterflies while the integer pipes idle.
+// Kept selectable for experiments (LGPU_K2_FPSUM=1).
+static int k2_fpsum() {
+    static const int on = [] { const char* e = getenv("LGPU_K2_FPSUM"); return e && atoi(e) ? 1 : 0; }();
+    return on;
+}
 // returns the stream for the integer chain (forked from `st`), or `st` itself when side streams are unavailable
 static cudaStream_t fork_side(const Ctx* c, cudaStream_t st, bool have_both) {
     if (!have_both) return st;
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
     const int nS = dg.nS;
     if (PRO == PRO_MODUP && p.skip_own && row < p.nq && row >= r0 && row < r0 + nS) return;   // own rows come from the NTT input
     const LimbConst L = p.limbs[limb];
-    const bool fpsum = FP && PRO == PRO_MODUP && dg.fp_src && (nS > 1 || !p.single_rule);
+    const bool fpsum = FP && PRO == PRO_MODUP && dg.fp_src == 2 && (nS > 1 || !p.single_rule);
     if (PRO == PRO_MODUP) {
         if (threadIdx.x < nS) s_c[threadIdx.x] = p.blob[(fpsum ? dg.off_cp : dg.off_c) + (size_t)limb * dg.ldc + threadIdx.x];
         if (threadIdx.x <= nS) s_vt[threadIdx.x] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + threadIdx.x];
@@ -501,7 +508,7 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         sp.dg[d].off_cp = (unsigned)m.off_c_plain;
         bool fps = true;
         for (int i = r0; i < r1; i++) fps = fps && c->h_limbs[i].fp_ok;
-        sp.dg[d].fp_src = fps ? 1 : 0;
+        sp.dg[d].fp_src = fps ? (unsigned short)(1 + k2_fpsum()) : 0;
     }
     {
         ProfScope ps(LGPU_KCLASS_MODUP, st, 8.0 * N * batch * (2.0 * nq), 1);
@@ -704,7 +711,7 @@ int moddown_ntt_fused(const Ctx* c, int levelQ, int levelP, const u64* acc, size
     {
         bool fps = true;
         for (int j = 0; j < np; j++) fps = fps && c->h_limbs[c->nQ + j].fp_ok;
-        sp.dg[0].fp_src = fps ? 1 : 0;
+        sp.dg[0].fp_src = fps ? (unsigned short)(1 + k2_fpsum()) : 0;
     }
     FzChunkParams cp;
     memset(&cp, 0, sizeof(cp));
