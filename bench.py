@@ -353,11 +353,11 @@ def gpu_main(args):
         if world == 1 and not args.no_cpu_baseline:
             # bounded CPU sample in a separate process (fork pool there; this process holds a CUDA context)
             try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
                                     "--preset", args.preset], capture_output=True, text=True, timeout=900)
                 ref = json.loads(r.stdout.strip().splitlines()[-1])
                 cpu = ref["cpu_baseline"]
-                cpu["sample"] = "1 step x %d ciphertext pairs (one per core), oracle port" % ref["config"]["pairs_per_step"]
+                cpu["sample"] = "1 warm-up + 1 timed step x %d ciphertext pairs (one per core), oracle port" % ref["config"]["pairs_per_step"]
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
         line = {

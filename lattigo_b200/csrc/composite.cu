@@ -658,8 +658,8 @@ static int ckks_mulrelin_rescale_chunk(const Ctx* c, int level, const u64* ctA, 
 static int batch_chunk() {
     static int v = [] {
         const char* e = getenv("LGPU_BATCH_CHUNK");
-        int x = e ? atoi(e) : 8;
-        return x > 0 ? x : 8;
+        int x = e ? atoi(e) : 16;
+        return x > 0 ? x : 16;
     }();
     return v;
 }
