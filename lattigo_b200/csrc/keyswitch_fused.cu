@@ -331,9 +331,12 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
         const bool own = d == own_d;
         const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow;
         const u64* e1 = e0 + p.evk_cs;
+        int dn = d + 1;
+        if (dn == own_d) dn++;
+        // first half of this thread's key words: requested before the last transform round so that the L2 latency
+        // is covered by that round instead of stalling the MAC
+        u64 k0[8], k1[8];
         if (!own) {
-            int dn = d + 1;
-            if (dn == own_d) dn++;
             if constexpr (FP) {
                 double* fsm = reinterpret_cast<double*>(sm);
                 const double fq = L.fq, fqinv = L.fqinv;
@@ -358,13 +361,11 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
                 double t2[15];
                 fp_load_tw<CL, 4, 4>(t2, tw, s1, chunk, tid);
                 __syncthreads();
-                if (dn < p.nd) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
-                }
                 fp_fwd_round_tw<CL, 4, 4>(fsm, t2, fq, fqinv, tid);
                 double t3[15];
                 fp_load_tw<CL, 8, 4>(t3, tw, s1, chunk, tid);
+#pragma unroll
+                for (int j = 0; j < 8; j++) { k0[j] = __ldg(e0 + j * T + tid); k1[j] = __ldg(e1 + j * T + tid); }
                 __syncthreads();
                 fp_fwd_round_tw<CL, 8, 4>(fsm, t3, fq, fqinv, tid);
             } else {
@@ -385,22 +386,29 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
                     for (int k = 0; k < 16; k++) sm[pad_idx(k * T + tid)] = raw[k];
                 }
                 __syncthreads();
-                if (dn < p.nd) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
-                }
                 fwd_round<CL, 4, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+#pragma unroll
+                for (int j = 0; j < 8; j++) { k0[j] = __ldg(e0 + j * T + tid); k1[j] = __ldg(e1 + j * T + tid); }
                 __syncthreads();
                 fwd_round<CL, 8, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
             }
             __syncthreads();
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) { k0[j] = __ldg(e0 + j * T + tid); k1[j] = __ldg(e1 + j * T + tid); }
         }
-        // MAC against evk[d]: the 32 key words of this thread are requested up front (two batches of 8 + 8)
+        // the tile of the next digit travels while the MAC runs
+        if (!own && dn < p.nd) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            u64 k0[8], k1[8];
+            u64 n0[8], n1[8];
+            if (h == 0) {   // second half of the key words, requested while the first half is consumed
 #pragma unroll
-            for (int j = 0; j < 8; j++) { const int idx = (h * 8 + j) * T + tid; k0[j] = __ldg(e0 + idx); k1[j] = __ldg(e1 + idx); }
+                for (int j = 0; j < 8; j++) { n0[j] = __ldg(e0 + (8 + j) * T + tid); n1[j] = __ldg(e1 + (8 + j) * T + tid); }
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int idx = (h * 8 + j) * T + tid;
@@ -416,6 +424,10 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
                     a0[idx] = v0 >= twoq ? v0 - twoq : v0;
                     a1[idx] = v1 >= twoq ? v1 - twoq : v1;
                 }
+            }
+            if (h == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) { k0[j] = n0[j]; k1[j] = n1[j]; }
             }
         }
         __syncthreads();
