@@ -444,6 +444,143 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K3, high-occupancy FP64 variant: 512 threads x 8 elements (four radix-8 rounds), <= 64 registers, 2 CTAs = 32 warps
+// per SM. The FP64 butterfly only reaches its pipe rate (0.46 warp-instr/clk/SMSP, tools/ubench/fp64_operands.cu) with
+// >= 4 warps per scheduler issuing it; the 256-thread variant leaves 2 warps per scheduler per CTA and half of them
+// sit in the integer MAC phase or at a barrier.
+// ------------------------------------------------------------------------------------------------------------
+template <int A>
+__device__ __forceinline__ void fp8_load_tw(double (&t)[7], const double* tw, int s1, int chunk, int tid) {
+    constexpr int LOB = 9 - A;
+    const int hi = tid >> LOB;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int twbase = (1 << (s1 + A + u)) + (chunk << (A + u)) + (hi << u);
+#pragma unroll
+        for (int m = 0; m < (1 << u); m++) t[(1 << u) - 1 + m] = __ldg(tw + twbase + m);
+    }
+}
+template <int A>
+__device__ __forceinline__ void fp8_round(double* sm, const double (&t)[7], double q, double qinv, int tid) {
+    constexpr int LOB = 9 - A;
+    const int hi = tid >> LOB, lo = tid & ((1 << LOB) - 1);
+    const int base = (hi << (12 - A)) + lo;
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = sm[fpad(base + (k << LOB))];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int half = 4 >> u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k & half) continue;
+            fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], q, qinv);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) sm[fpad(base + (k << LOB))] = x[k];
+}
+
+__global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8_kernel(KsChunkParams p) {
+    constexpr int CL = 12, T = 512;
+    extern __shared__ u64 smem[];
+    double* fsm = reinterpret_cast<double*>(smem);
+    u64* a0 = smem + 4096 + 256 + 8;
+    u64* a1 = a0 + 4096;
+    const int b = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+    const int limb = p.rm.limb[blockIdx.z];
+    const int row = p.rm.drow[blockIdx.z];
+    const LimbConst L = p.limbs[limb];
+    const int s1 = p.logN - CL;
+    const int N = 1 << p.logN;
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
+    const double fq = L.fq, fqinv = L.fqinv;
+    const double* tw = L.ftw_fwd;
+    const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
+    const u64* P1row = p.P1 + (size_t)b * p.p1_bs + (size_t)row * N + ((size_t)chunk << CL);
+    const u64* xin = p.cx + (size_t)b * p.cx_bs + (size_t)row * p.cx_rs + ((size_t)chunk << CL);
+    const int own_d = row < p.nq ? row / p.k : -1;
+    u64 raw[8];
+    {
+        const int d0 = own_d == 0 ? 1 : 0;
+        if (d0 < p.nd) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d0 * p.p1_ds + k * T + tid];
+        }
+    }
+    for (int d = 0; d < p.nd; d++) {
+        const bool own = d == own_d;
+        const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow;
+        const u64* e1 = e0 + p.evk_cs;
+        int dn = d + 1;
+        if (dn == own_d) dn++;
+        if (!own) {
+            {
+                double x[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)raw[k]);
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int half = 4 >> u;
+                    const int twbase = (1 << (s1 + u)) + (chunk << u);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (k & half) continue;
+                        fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), fq, fqinv);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) fsm[fpad(k * T + tid)] = x[k];
+            }
+            double t[7];
+            fp8_load_tw<3>(t, tw, s1, chunk, tid);
+            __syncthreads();
+            fp8_round<3>(fsm, t, fq, fqinv, tid);
+            fp8_load_tw<6>(t, tw, s1, chunk, tid);
+            __syncthreads();
+            fp8_round<6>(fsm, t, fq, fqinv, tid);
+            fp8_load_tw<9>(t, tw, s1, chunk, tid);
+            __syncthreads();
+            fp8_round<9>(fsm, t, fq, fqinv, tid);
+            __syncthreads();
+            if (dn < p.nd) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            u64 k0[4], k1[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { k0[j] = __ldg(e0 + (h * 4 + j) * T + tid); k1[j] = __ldg(e1 + (h * 4 + j) * T + tid); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int idx = (h * 4 + j) * T + tid;
+                const u64 x = own ? xin[idx] : fp_canon(fsm[fpad(idx)], fq, fqinv);
+                const u64 m0 = mred_lazy(k0[j], x, q, qinv);
+                const u64 m1 = mred_lazy(k1[j], x, q, qinv);
+                if (d == 0) { a0[idx] = m0; a1[idx] = m1; }
+                else {
+                    u64 v0 = a0[idx] + m0, v1 = a1[idx] + m1;
+                    a0[idx] = v0 >= twoq ? v0 - twoq : v0;
+                    a1[idx] = v1 >= twoq ? v1 - twoq : v1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    u64* o0 = p.acc + (size_t)b * p.acc_bs + (size_t)row * N + ((size_t)chunk << CL);
+    u64* o1 = o0 + p.acc_cs;
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+        const int idx = kk * T + tid;
+        const u64 v0 = a0[idx], v1 = a1[idx];
+        o0[idx] = cred(v0 >= twoq ? v0 - twoq : v0, q);
+        o1[idx] = cred(v1 >= twoq ? v1 - twoq : v1, q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------------------
 bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
@@ -571,8 +708,14 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         }
         // algorithmic bytes: P1 read once + accumulators written once + evk once per launch
         ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * fp.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
-        LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ks_chunk_mac_kernel<true><<<dim3(batch, chunks, fp.nrows), 256, smem, st>>>(cp);
+        static const int k3v = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 8; }();
+        if (k3v == 8) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8_kernel<<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        } else {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_kernel<true><<<dim3(batch, chunks, fp.nrows), 256, smem, st>>>(cp);
+        }
         LGPU_CUDA_OK(cudaGetLastError());
     }
     join_side(c, st, sint);

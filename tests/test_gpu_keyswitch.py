@@ -366,3 +366,70 @@ def test_ckks_mulrelin_rescale_full_size_pn16qp1761():
         r = ev_o.Rescale(ev_o.MulRelinNew([ah[i, 0], ah[i, 1]], [bh[i, 0], bh[i, 1]]))
         assert np.array_equal(oh[i, 0], r[0]) and np.array_equal(oh[i, 1], r[1]), i
     ctx.close()
+
+
+def test_ringqp_dispatch(small):
+    """ringqp.Ring ops = RingQ op then RingP op (ring/ringqp/operations.go:8-316)."""
+    lb, ctx, params, q, p = small
+    N = params.N()
+    rng = np.random.default_rng(21)
+    levelQ, levelP = 4, 1
+    rqp = lb.RingQP(ctx).AtLevel(levelQ, levelP)
+    oq, op = params.ringQ.AtLevel(levelQ), params.ringP.AtLevel(levelP)
+    aq, ap = H.rand_poly(q[: levelQ + 1], N, rng), H.rand_poly(p[: levelP + 1], N, rng)
+    bq, bp = H.rand_poly(q[: levelQ + 1], N, rng), H.rand_poly(p[: levelP + 1], N, rng)
+    A = lb.PolyQP(ctx.to_device(aq), ctx.to_device(ap)); B = lb.PolyQP(ctx.to_device(bq), ctx.to_device(bp))
+    C = rqp.NewPoly()
+    for name in ("Add", "Sub", "MulCoeffsMontgomery", "MulCoeffsMontgomeryLazy"):
+        wq, wp = np.zeros_like(aq), np.zeros_like(ap)
+        getattr(oq, name)(aq, bq, wq); getattr(op, name)(ap, bp, wp)
+        getattr(rqp, name)(A, B, C)
+        assert np.array_equal(ctx.to_host(C.Q), wq) and np.array_equal(ctx.to_host(C.P), wp), name
+    wq, wp = np.zeros_like(aq), np.zeros_like(ap)
+    oq.NTT(aq, wq); op.NTT(ap, wp)
+    rqp.NTT(A, C)
+    assert np.array_equal(ctx.to_host(C.Q), wq) and np.array_equal(ctx.to_host(C.P), wp)
+    rqp.INTT(C, C)
+    assert np.array_equal(ctx.to_host(C.Q), aq) and np.array_equal(ctx.to_host(C.P), ap)
+
+
+def test_bgv_rotate_full_size_n15qp880():
+    """BASELINE config 4 shape: BGV N15QP880 RotateColumns = Evaluator.Automorphism (key-switch + NTT-domain
+    permutation), batch of ciphertexts, bit-exact vs the oracle for 2 of them + batch consistency."""
+    import torch
+    lb = _lb()
+    from lattigo_b200 import params as presets
+    s = presets.PRESETS["BGV_N15QP880"]
+    logN, q, p = s["logN"], s["Q"], s["P"]
+    ctx = lb.Context(logN, q, p)
+    N = 1 << logN
+    level, levelP = len(q) - 1, len(p) - 1
+    nd = (level + levelP + 1) // (levelP + 1)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+
+    def rand_rows(mods, lead):
+        out = torch.empty(tuple(lead) + (len(mods), N), dtype=torch.int64, device="cuda")
+        for i, m in enumerate(mods):
+            out[..., i, :] = torch.randint(0, m, tuple(lead) + (N,), generator=g, device="cuda", dtype=torch.int64)
+        return out
+
+    gk_t = rand_rows(q + p, (nd, 1, 2))
+    gk = lb.GadgetCiphertext(ctx, gk_t, level, levelP)
+    ev = lb.Evaluator(ctx)
+    params = O.Parameters(logN, q, p)
+    galEl = params.GaloisElement(3)
+    batch = 5
+    ct = rand_rows(q, (batch, 2))
+    out = torch.zeros_like(ct)
+    ev.Automorphism(ct, galEl, gk, out)
+    one = torch.zeros_like(ct[3:4])
+    ev.Automorphism(ct[3:4].contiguous(), galEl, gk, one)
+    assert torch.equal(out[3:4], one)
+    gk_o = O.GadgetCiphertext(ctx.to_host(gk_t), level + 1, levelP + 1)
+    ev_o = O.Evaluator(params)
+    cth, oh = ctx.to_host(ct[:2]), ctx.to_host(out[:2])
+    for i in range(2):
+        w = [np.zeros((level + 1, N), dtype=U64) for _ in range(2)]
+        ev_o.Automorphism([cth[i, 0], cth[i, 1]], galEl, gk_o, w)
+        assert np.array_equal(oh[i, 0], w[0]) and np.array_equal(oh[i, 1], w[1]), i
+    ctx.close()
