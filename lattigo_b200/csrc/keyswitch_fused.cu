@@ -156,9 +156,12 @@ __device__ __forceinline__ u64 ks_ext(const u64 (&y)[NSMAX], int nS, int v, cons
 }
 
 enum { PRO_MODUP = 0, PRO_BCAST = 1 };
+#ifndef KS_STRIDED_MINB
+#define KS_STRIDED_MINB 4
+#endif
 
 template <int RL, int NSMAX, bool FP, int PRO>
-__global__ void __launch_bounds__(256) ks_strided_kernel(KsStridedParams p) {
+__global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStridedParams p) {
     constexpr int R = 1 << RL;
     __shared__ u64 s_c[NSMAX];
     __shared__ u64 s_vt[NSMAX + 1];
@@ -778,14 +781,91 @@ __global__ void __launch_bounds__(256, 2) fz_chunk_epi_kernel(FzChunkParams p) {
         fwd_round<CL, 8, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
     }
     __syncthreads();
-#pragma unroll 4
-    for (int kk = 0; kk < 16; kk++) {
-        const int idx = kk * T + tid;
-        u64 x;
-        if (FP) x = fp_canon(reinterpret_cast<double*>(sm)[fpad(idx)], L.fq, L.fqinv);
-        else x = sm[pad_idx(idx)];
-        u64 r = mred(x + twoq - A[idx], sc, q, qinv);
-        if (D) r = cred(r + D[idx], q);
+    // loads of a whole batch are issued before any store (out may alias A or D, so the compiler cannot hoist them itself)
+    constexpr int EB = 8;
+#pragma unroll 1
+    for (int k0 = 0; k0 < 16; k0 += EB) {
+        u64 a[EB], d[EB];
+#pragma unroll
+        for (int j = 0; j < EB; j++) {
+            const int idx = (k0 + j) * T + tid;
+            a[j] = A[idx];
+            d[j] = D ? D[idx] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < EB; j++) {
+            const int idx = (k0 + j) * T + tid;
+            u64 x;
+            if (FP) x = fp_canon(reinterpret_cast<double*>(sm)[fpad(idx)], L.fq, L.fqinv);
+            else x = sm[pad_idx(idx)];
+            u64 r = mred(x + twoq - a[j], sc, q, qinv);
+            if (D) r = cred(r + d[j], q);
+            out[idx] = r;
+        }
+    }
+}
+
+// high-occupancy FP64 variant of the same kernel (512 threads x 8 elements, see ks_chunk_mac_fp8_kernel)
+__global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams p) {
+    constexpr int CL = 12, T = 512;
+    extern __shared__ u64 smem[];
+    double* fsm = reinterpret_cast<double*>(smem);
+    const int chunk = blockIdx.x, z = blockIdx.z, tid = threadIdx.x;
+    const int limb = p.rm.limb[blockIdx.y];
+    const int row = p.rm.drow[blockIdx.y];
+    const LimbConst L = p.limbs[limb];
+    const int s1 = p.logN - CL;
+    const int N = 1 << p.logN;
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
+    const double fq = L.fq, fqinv = L.fqinv;
+    const double* tw = L.ftw_fwd;
+    const u64 sc = p.s[blockIdx.y];
+    const int zc = z / p.nb, zb = z % p.nb;
+    const size_t roff = (size_t)row * N + ((size_t)chunk << CL);
+    const u64* src = p.P1 + (size_t)z * p.p1_bs + roff;
+    const u64* A = p.A + (size_t)zc * p.a_cs + (size_t)zb * p.a_bs + roff;
+    const u64* D = p.D ? p.D + (size_t)zc * p.d_cs + (size_t)zb * p.d_bs + roff : nullptr;
+    u64* out = p.out + (size_t)zc * p.o_cs + (size_t)zb * p.o_bs + roff;
+    {
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)src[k * T + tid]);
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int half = 4 >> u;
+            const int twbase = (1 << (s1 + u)) + (chunk << u);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k & half) continue;
+                fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), fq, fqinv);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) fsm[fpad(k * T + tid)] = x[k];
+    }
+    double t[7];
+    fp8_load_tw<3>(t, tw, s1, chunk, tid);
+    __syncthreads();
+    fp8_round<3>(fsm, t, fq, fqinv, tid);
+    fp8_load_tw<6>(t, tw, s1, chunk, tid);
+    __syncthreads();
+    fp8_round<6>(fsm, t, fq, fqinv, tid);
+    fp8_load_tw<9>(t, tw, s1, chunk, tid);
+    __syncthreads();
+    fp8_round<9>(fsm, t, fq, fqinv, tid);
+    u64 a[8], d[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        a[j] = A[j * T + tid];
+        d[j] = D ? D[j * T + tid] : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int idx = j * T + tid;
+        const u64 x = fp_canon(fsm[fpad(idx)], fq, fqinv);
+        u64 r = mred(x + twoq - a[j], sc, q, qinv);
+        if (D) r = cred(r + d[j], q);
         out[idx] = r;
     }
 }
@@ -793,6 +873,12 @@ __global__ void __launch_bounds__(256, 2) fz_chunk_epi_kernel(FzChunkParams p) {
 template <bool FP>
 static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
     const size_t smem = (size_t)(4096 + 256 + 8) * sizeof(u64);
+    static const int v8 = [] { const char* e = getenv("LGPU_FZ_VARIANT"); return e ? atoi(e) : 8; }();
+    if (FP && v8 == 8) {
+        fz_chunk_epi_fp8_kernel<<<grid, 512, smem, st>>>(p);
+        LGPU_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     fz_chunk_epi_kernel<FP><<<grid, 256, smem, st>>>(p);
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
