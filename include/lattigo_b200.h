@@ -152,6 +152,22 @@ int lgpu_automorphism_ntt(lgpu_ctx* ctx, int ring, int level, const uint64_t* in
 int lgpu_automorphism(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t gal_el, uint64_t* out,
                       int batch, size_t batch_stride, void* stream);
 
+/* Ring.Shift (ring/operations.go:278-282): out[i] = in[(i + k) mod N] on rows 0..level. In-place allowed. */
+int lgpu_shift(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, int k, uint64_t* out,
+               int batch, size_t batch_stride, void* stream);
+/* Ring.MultByMonomial (ring/operations.go:306-363): out = in * X^k, k > -2N, with the reference's literal
+ * `q - x` negation (a wrapped zero coefficient becomes q). In-place allowed. */
+int lgpu_mult_by_monomial(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, int k, uint64_t* out,
+                          int batch, size_t batch_stride, void* stream);
+/* MapSmallDimensionToLargerDimensionNTT (ring/operations.go:380-392): large[r][i*gap + w] = small[r][i],
+ * `rows` contiguous rows of n_small resp. n_large words. */
+int lgpu_map_small_dimension_to_larger_dimension_ntt(lgpu_ctx* ctx, const uint64_t* pol_small, int n_small,
+                                                     uint64_t* pol_large, int n_large, int rows, void* stream);
+/* ringqp.Ring.ExtendBasisSmallNormAndCenter (ring/ringqp/operations.go:325-351): reads row 0 of poly_in_q,
+ * writes level_p+1 rows of poly_out_p (the copy polyOutQ = polyInQ is the caller's). */
+int lgpu_extend_basis_small_norm_and_center(lgpu_ctx* ctx, const uint64_t* poly_in_q, int level_p, uint64_t* poly_out_p,
+                                            int batch, size_t stride_q, size_t stride_p, void* stream);
+
 /* ---- RNS basis extension (ring/basis_extension.go) -------------------------------------------------------
  * polQ has levelQ+1 rows, polP has levelP+1 rows; `batch` polynomials with the given strides (words). */
 /* BasisExtender.ModUpQtoP (:177-190) / ModUpPtoQ (:195-209): outputs are the reference's exact (non-canonical,

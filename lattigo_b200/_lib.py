@@ -55,6 +55,10 @@ def lib():
             "lgpu_automorphism_ntt_with_index": [vp, i, i, vp, vp, vp, i, i, z, vp],
             "lgpu_automorphism_ntt": [vp, i, i, vp, u64, vp, i, z, vp],
             "lgpu_automorphism": [vp, i, i, vp, u64, vp, i, z, vp],
+            "lgpu_shift": [vp, i, i, vp, i, vp, i, z, vp],
+            "lgpu_mult_by_monomial": [vp, i, i, vp, i, vp, i, z, vp],
+            "lgpu_map_small_dimension_to_larger_dimension_ntt": [vp, vp, i, vp, i, i, vp],
+            "lgpu_extend_basis_small_norm_and_center": [vp, vp, i, vp, i, z, z, vp],
             "lgpu_modup_qtop": [vp, i, i, vp, vp, i, z, z, vp],
             "lgpu_modup_ptoq": [vp, i, i, vp, vp, i, z, z, vp],
             "lgpu_moddown_qp_to_q": [vp, i, i, vp, vp, vp, i, z, z, vp],

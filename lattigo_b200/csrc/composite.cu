@@ -266,9 +266,36 @@ __global__ void __launch_bounds__(256) auto_coeff_kernel(AutoCoeffParams p) {
     const u64 v = in[i];
     out[idx] = neg ? (q - v) : v;     // in[i]*(tmp^1) | (q - in[i])*tmp
 }
+// ConjugateInvariant ring, ring/automorphism.go:123-155: i runs over [0, 2N); only images below N are written, sources
+// in [N, 2N) wrap to 2N - i with a sign flip. i -> i*gen mod 2N is a bijection, so every output is written exactly once.
+__global__ void __launch_bounds__(256) auto_coeff_ci_kernel(AutoCoeffParams p) {
+    const u64 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 N = (u64)p.n;
+    if (i >= 2 * N) return;
+    const u64 raw = i * p.gen;
+    const u64 idx = raw & (2 * N - 1);
+    if (idx >= N) return;
+    u64 neg = (raw >> (p.logN + 1)) & 1;
+    u64 src = i;
+    if (src >= N) { src = 2 * N - src; neg ^= 1; }
+    const u64 q = p.limbs[p.rm.limb[blockIdx.y]].q;
+    const u64* in = p.in + (size_t)blockIdx.z * p.in_bs + (size_t)blockIdx.y * p.in_rs;
+    u64* out = p.out + (size_t)blockIdx.z * p.out_bs + (size_t)blockIdx.y * p.out_rs;
+    const u64 v = in[src];
+    out[idx] = neg ? (q - v) : v;
+}
 int automorphism_coeff(const Ctx* c, const RowMap& rm, CSpan in, u64 gen, Span out, int batch, cudaStream_t st) {
-    if (c->ring_type != 0) { set_error("coefficient-domain automorphism is implemented for the Standard ring only"); return -1; }
     if (in.p == out.p) { set_error("Automorphism cannot be in-place"); return -1; }
+    if (c->ring_type != 0) {
+        AutoCoeffParams p;
+        p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.in_rs = in.row_stride; p.in_bs = in.batch_stride;
+        p.out = out.p; p.out_rs = out.row_stride; p.out_bs = out.batch_stride; p.gen = gen; p.n = c->N; p.logN = c->logN;
+        ProfScope ps(LGPU_KCLASS_AUTOMORPHISM, st, 16.0 * c->N * rm.nrows * batch, 1);
+        dim3 grid((2 * c->N + 255) / 256, rm.nrows, batch);
+        auto_coeff_ci_kernel<<<grid, 256, 0, st>>>(p);
+        LGPU_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     AutoCoeffParams p;
     p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.in_rs = in.row_stride; p.in_bs = in.batch_stride;
     p.out = out.p; p.out_rs = out.row_stride; p.out_bs = out.batch_stride; p.gen = gen; p.n = c->N; p.logN = c->logN;

@@ -150,6 +150,8 @@ int launch_vecop(const Ctx* c, const RowMap& rm, int op, CSpan p1, CSpan p2, Spa
 
 // ntt_fp64.cu
 bool fp64_ntt_supported(const Ctx* c);
+// conjugate-invariant ring (ntt_ci.cu); lazy selects NTTConjugateInvariantLazy / INTTConjugateInvariantLazy
+int launch_ntt_ci(const Ctx* c, const RowMap& rm, bool inverse, CSpan in, Span out, int batch, int lazy, cudaStream_t st);
 int launch_ntt_fp64(const Ctx* c, const RowMap& rm, bool inverse, CSpan in, Span out, int batch, cudaStream_t st);
 
 // basisext.cu

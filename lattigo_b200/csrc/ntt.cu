@@ -357,7 +357,6 @@ static int fast_variant(const Ctx* c, const RowMap& rm, bool inverse) {
 static int check_common(const Ctx* c, const RowMap& rm, int batch) {
     if (c->logN < 4 || c->logN > 17) { set_error("NTT requires 16 <= N <= 2^17"); return -1; }
     if (rm.nrows <= 0 || rm.nrows > kMaxRows || batch <= 0 || batch > 65535) { set_error("bad rows/batch"); return -1; }
-    if (c->ring_type != 0) { set_error("conjugate-invariant NTT is not implemented on device"); return -1; }
     return 0;
 }
 
@@ -377,6 +376,7 @@ static int launch_intt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, i
 
 int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
     if (check_common(c, rm, batch)) return -1;
+    if (c->ring_type != 0) return launch_ntt_ci(c, rm, false, in, out, batch, mode == NTT_EXACT_LAZY, st);
     RowMap fp, rest;
     if (mode == NTT_CANONICAL && split_rows_fp64(c, rm, fp, rest)) {
         {
@@ -391,6 +391,7 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
 
 int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
     if (check_common(c, rm, batch)) return -1;
+    if (c->ring_type != 0) return launch_ntt_ci(c, rm, true, in, out, batch, mode == NTT_EXACT_LAZY, st);
     RowMap fp, rest;
     if (mode != NTT_REFERENCE_ARITH && split_rows_fp64(c, rm, fp, rest)) {
         {

@@ -66,6 +66,7 @@ class Context:
         self.Q = [int(x) for x in Q]
         self.P = [int(x) for x in P]
         self.device = device
+        self.ring_type = ring_type        # 0 = ring.Standard, 1 = ring.ConjugateInvariant (NthRoot = 4N)
         qa = np.array(self.Q, dtype=np.uint64)
         pa = np.array(self.P, dtype=np.uint64) if self.P else None
         h = ctypes.c_void_p()
@@ -91,7 +92,8 @@ class Context:
 
     # table read-back (host)
     def table(self, ring: int, limb: int, kind: int) -> np.ndarray:
-        n = {0: 6, 1: self.N, 2: self.N, 3: max(limb, 1)}[kind]
+        half = self.N << (1 if self.ring_type else 0)            # NthRoot / 2 root-table entries
+        n = {0: 6, 1: half, 2: half, 3: max(limb, 1)}[kind]
         out = np.zeros(n, dtype=np.uint64)
         _lib.check(_lib.lib().lgpu_ring_get_table(self.h, ring, limb, kind, out.ctypes.data, n))
         return out
@@ -227,3 +229,80 @@ class Ring:
 
     MulScalarBigint = MulScalar                     # ring/operations.go:231
     MulScalarBigintThenAdd = MulScalarThenAdd       # ring/operations.go:240
+
+    def MulScalarThenSub(self, p1, scalar: int, p2):   # ring/operations.go:223
+        self._vec("MulScalarMontgomeryThenAdd", p1, None, p2, [((q - scalar % q) << 64) % q for q in self._lvl_mods()])
+
+    def MulRNSScalarMontgomery(self, p1, scalar: Sequence[int], p2):   # ring/operations.go:216
+        self._vec("MulScalarMontgomery", p1, None, p2, list(scalar)[: self.level + 1])
+
+    def _halves(self, name, p1, s0, s1, p2):
+        # the *DoubleRNSScalar family: one SubRing op on coefficients [0, N/2), another on [N/2, N)
+        assert p2.dim() == 2, "DoubleRNSScalar ops take a single (limbs, N) polynomial"
+        h = self.ctx.N >> 1
+        for i, sr in enumerate(self.SubRings[: self.level + 1]):
+            sr._vec(name, p1[i, :h], None, p2[i, :h], s0[i])
+            sr._vec(name, p1[i, h:], None, p2[i, h:], s1[i])
+
+    def AddDoubleRNSScalar(self, p1, scalar0, scalar1, p2):        # ring/operations.go:167
+        self._halves("AddScalar", p1, scalar0, scalar1, p2)
+
+    def SubDoubleRNSScalar(self, p1, scalar0, scalar1, p2):        # ring/operations.go:177
+        self._halves("SubScalar", p1, scalar0, scalar1, p2)
+
+    def MulDoubleRNSScalar(self, p1, scalar0, scalar1, p2):        # ring/operations.go:250
+        m = self._lvl_mods()
+        self._halves("MulScalarMontgomery", p1, [(int(a) << 64) % q for a, q in zip(scalar0, m)], [(int(a) << 64) % q for a, q in zip(scalar1, m)], p2)
+
+    def MulDoubleRNSScalarThenAdd(self, p1, scalar0, scalar1, p2):  # ring/operations.go:260
+        m = self._lvl_mods()
+        self._halves("MulScalarMontgomeryThenAdd", p1, [(int(a) << 64) % q for a, q in zip(scalar0, m)], [(int(a) << 64) % q for a, q in zip(scalar1, m)], p2)
+
+    def EvalPolyScalar(self, p1: Sequence, scalar: int, p2):       # ring/operations.go:269
+        p2[..., : self.level + 1, :].copy_(p1[-1][..., : self.level + 1, :])
+        for i in range(len(p1) - 1, 0, -1):
+            self.MulScalar(p2, scalar, p2)
+            self.Add(p2, p1[i - 1], p2)
+
+    def Shift(self, p1, k: int, p2):                # ring/operations.go:278
+        b, bs = self._batch(p2)
+        _lib.check(_lib.lib().lgpu_shift(self.ctx.h, self.which, self.level, _dptr(p1), int(k), _dptr(p2), b, bs, _stream()))
+
+    def MultByMonomial(self, p1, k: int, p2):       # ring/operations.go:306
+        b, bs = self._batch(p2)
+        _lib.check(_lib.lib().lgpu_mult_by_monomial(self.ctx.h, self.which, self.level, _dptr(p1), int(k), _dptr(p2), b, bs, _stream()))
+
+    def MulByVectorMontgomery(self, p1, vector, p2):               # ring/operations.go:366
+        for i, sr in enumerate(self.SubRings[: self.level + 1]): sr._vec("MulCoeffsMontgomery", p1[i], vector, p2[i])
+
+    def MulByVectorMontgomeryThenAddLazy(self, p1, vector, p2):    # ring/operations.go:373
+        for i, sr in enumerate(self.SubRings[: self.level + 1]): sr._vec("MulCoeffsMontgomeryThenAddLazy", p1[i], vector, p2[i])
+
+    # ring/automorphism.go and ring/scaling.go (thin wrappers over the C ABI; batch = leading dimension)
+    def AutomorphismNTTIndex(self, galEl: int):     # ring/automorphism.go:12
+        idx = self.ctx.new_poly(1)[0]
+        _lib.check(_lib.lib().lgpu_automorphism_ntt_index(self.ctx.h, int(galEl), _dptr(idx), _stream()))
+        return idx
+
+    def AutomorphismNTTWithIndex(self, polIn, index, polOut):      # ring/automorphism.go:50
+        b, bs = self._batch(polOut)
+        _lib.check(_lib.lib().lgpu_automorphism_ntt_with_index(self.ctx.h, self.which, self.level, _dptr(polIn), _dptr(index), _dptr(polOut), 0, b, bs, _stream()))
+
+    def AutomorphismNTTWithIndexThenAddLazy(self, polIn, index, polOut):   # ring/automorphism.go:82
+        b, bs = self._batch(polOut)
+        _lib.check(_lib.lib().lgpu_automorphism_ntt_with_index(self.ctx.h, self.which, self.level, _dptr(polIn), _dptr(index), _dptr(polOut), 1, b, bs, _stream()))
+
+    def AutomorphismNTT(self, polIn, galEl: int, polOut):          # ring/automorphism.go:38
+        b, bs = self._batch(polOut)
+        _lib.check(_lib.lib().lgpu_automorphism_ntt(self.ctx.h, self.which, self.level, _dptr(polIn), int(galEl), _dptr(polOut), b, bs, _stream()))
+
+    def Automorphism(self, polIn, galEl: int, polOut):             # ring/automorphism.go:113
+        b, bs = self._batch(polOut)
+        _lib.check(_lib.lib().lgpu_automorphism(self.ctx.h, self.which, self.level, _dptr(polIn), int(galEl), _dptr(polOut), b, bs, _stream()))
+
+
+def MapSmallDimensionToLargerDimensionNTT(ctx: "Context", polSmall, polLarge):   # ring/operations.go:380
+    rows = min(polSmall.shape[0], polLarge.shape[0])
+    assert polSmall.dim() == 2 and polLarge.dim() == 2
+    _lib.check(_lib.lib().lgpu_map_small_dimension_to_larger_dimension_ntt(ctx.h, _dptr(polSmall), polSmall.shape[1], _dptr(polLarge), polLarge.shape[1],
+                                                                          rows, _stream()))

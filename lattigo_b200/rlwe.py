@@ -170,6 +170,25 @@ class Evaluator:
         level = ctIn.shape[-2] - 1
         _lib.check(_lib.lib().lgpu_evaluator_automorphism(self.ctx.h, level, _dptr(ctIn), galEl, gk.ref(), _dptr(decomp), _dptr(ctOut), b, _stream()))
 
+    def AutomorphismHoistedLazy(self, levelQ, ctIn, decomp, galEl: int, gk: GadgetCiphertext, ctQP_Q, ctQP_P):
+        """Evaluator.AutomorphismHoistedLazy (core/rlwe/evaluator_automorphism.go:107-165), ctQP.IsNTT branch: the result
+        stays modulo QP, scaled by P. ctIn: (2, levelQ+1, N); decomp: DecomposeNTT output; ctQP_Q / ctQP_P: pairs of
+        (levelQ+1, N) / (levelP+1, N) output polynomials. Same op sequence as the reference, each op one C-ABI call."""
+        ctx = self.ctx
+        levelP = gk.LevelP()
+        ringQ = ctx.ringQ.AtLevel(levelQ); ringP = ctx.ringP.AtLevel(levelP)
+        tQ = [ringQ.NewPoly(), ringQ.NewPoly()]
+        tP = [ringP.NewPoly(), ringP.NewPoly()]
+        self.GadgetProductHoistedLazy(levelQ, decomp, gk, tQ[0], tP[0], tQ[1], tP[1])
+        index = ringQ.AutomorphismNTTIndex(galEl)
+        ringQ.AutomorphismNTTWithIndex(tQ[1], index, ctQP_Q[1]); ringP.AutomorphismNTTWithIndex(tP[1], index, ctQP_P[1])
+        if levelP > -1:
+            Pprod = 1
+            for pj in ctx.P[: levelP + 1]: Pprod *= pj
+            ringQ.MulScalarBigint(ctIn[0], Pprod, tQ[1])
+        ringQ.Add(tQ[0], tQ[1], tQ[0])
+        ringQ.AutomorphismNTTWithIndex(tQ[0], index, ctQP_Q[0]); ringP.AutomorphismNTTWithIndex(tP[0], index, ctQP_P[0])
+
     def Relinearize(self, ctIn, rlk: GadgetCiphertext, ctOut):
         b, _ = _bs(ctIn, 3)
         level = ctIn.shape[-2] - 1

@@ -454,6 +454,18 @@ void lo_automorphism_ntt_row(const u64 *in, const u64 *index, u64 *out, int N, i
     if (accumulate) for (int j = 0; j < N; j++) out[j] += in[index[j]];
     else            for (int j = 0; j < N; j++) out[j] = in[index[j]];
 }
+/* Ring.Automorphism (coefficient domain, ConjugateInvariant ring): ring/automorphism.go:123-155 */
+void lo_automorphism_row_ci(const u64 *in, u64 *out, int N, u64 gen, u64 q) {
+    u64 n = (u64)N, mask = 2 * n - 1; int logN = 0; while (((u64)1 << logN) <= mask) logN++;   /* bits.Len64(mask) */
+    for (u64 i = 0; i < 2 * n; i++) {
+        u64 raw = i * gen, index = raw & mask, tmp = (raw >> logN) & 1;
+        if (index < n) {
+            u64 idx = i;
+            if (idx >= n) { idx = 2 * n - idx; tmp ^= 1; }
+            out[index] = in[idx] * (tmp ^ 1) | (q - in[idx]) * tmp;
+        }
+    }
+}
 /* Ring.Automorphism (coefficient domain, Standard ring): ring/automorphism.go:158-175 */
 void lo_automorphism_row(const u64 *in, u64 *out, int N, u64 gen, u64 q) {
     u64 mask = (u64)N - 1; int logN = 0; while ((1 << logN) < N) logN++;

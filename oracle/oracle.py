@@ -77,6 +77,7 @@ def lib():
         L.lo_automorphism_ntt_index.argtypes = [i, u, u, p]
         L.lo_automorphism_ntt_row.argtypes = [p, p, p, i, i]
         L.lo_automorphism_row.argtypes = [p, p, i, u, u]
+        L.lo_automorphism_row_ci.argtypes = [p, p, i, u, u]
         for name in ("lo_mred", "lo_mred_lazy"):
             f = getattr(L, name); f.argtypes = [u, u, u, u]; f.restype = u
         for name in ("lo_mform", "lo_mform_lazy", "lo_bred_add", "lo_bred_add_lazy"):
@@ -358,6 +359,76 @@ class Ring:
     def MulScalarThenAdd(self, p1, scalar, p2):   # ring/operations.go:208-213
         self._op("MulScalarMontgomeryThenAdd", p1, None, p2, [mform(scalar % s.Modulus, s.Modulus) for s in self.SubRings[: self.level + 1]])
 
+    def _mods(self): return [s.Modulus for s in self.SubRings[: self.level + 1]]
+
+    def AddDoubleRNSScalar(self, p1, scalar0, scalar1, p2):      # ring/operations.go:167-173
+        h = self.N() >> 1
+        for i, s in enumerate(self.SubRings[: self.level + 1]):
+            s.vecop("AddScalar", p1[i][:h], None, p2[i][:h], scalar0[i])
+            s.vecop("AddScalar", p1[i][h:], None, p2[i][h:], scalar1[i])
+
+    def SubDoubleRNSScalar(self, p1, scalar0, scalar1, p2):      # ring/operations.go:177-183
+        h = self.N() >> 1
+        for i, s in enumerate(self.SubRings[: self.level + 1]):
+            s.vecop("SubScalar", p1[i][:h], None, p2[i][:h], scalar0[i])
+            s.vecop("SubScalar", p1[i][h:], None, p2[i][h:], scalar1[i])
+
+    def MulRNSScalarMontgomery(self, p1, scalar, p2):           # ring/operations.go:216-220
+        self._op("MulScalarMontgomery", p1, None, p2, list(scalar))
+
+    def MulScalarThenSub(self, p1, scalar, p2):                 # ring/operations.go:223-228
+        self._op("MulScalarMontgomeryThenAdd", p1, None, p2,
+                 [mform(s.Modulus - scalar % s.Modulus, s.Modulus) for s in self.SubRings[: self.level + 1]])
+
+    MulScalarBigint = MulScalar                                 # ring/operations.go:231-237
+    MulScalarBigintThenAdd = MulScalarThenAdd                   # ring/operations.go:240-246
+
+    def MulDoubleRNSScalar(self, p1, scalar0, scalar1, p2):     # ring/operations.go:250-256
+        h = self.N() >> 1
+        for i, s in enumerate(self.SubRings[: self.level + 1]):
+            s.vecop("MulScalarMontgomery", p1[i][:h], None, p2[i][:h], mform(scalar0[i], s.Modulus))
+            s.vecop("MulScalarMontgomery", p1[i][h:], None, p2[i][h:], mform(scalar1[i], s.Modulus))
+
+    def MulDoubleRNSScalarThenAdd(self, p1, scalar0, scalar1, p2):   # ring/operations.go:260-266
+        h = self.N() >> 1
+        for i, s in enumerate(self.SubRings[: self.level + 1]):
+            s.vecop("MulScalarMontgomeryThenAdd", p1[i][:h], None, p2[i][:h], mform(scalar0[i], s.Modulus))
+            s.vecop("MulScalarMontgomeryThenAdd", p1[i][h:], None, p2[i][h:], mform(scalar1[i], s.Modulus))
+
+    def EvalPolyScalar(self, p1, scalar, p2):                   # ring/operations.go:269-275
+        p2[: self.level + 1] = p1[-1][: self.level + 1]
+        for i in range(len(p1) - 1, 0, -1):
+            self.MulScalar(p2, scalar, p2)
+            self.Add(p2, p1[i - 1], p2)
+
+    def Shift(self, p1, k, p2):                                 # ring/operations.go:278-282 (all rows of p1)
+        n = self.N()
+        k %= n
+        for i in range(p1.shape[0]):
+            p2[i] = np.concatenate([p1[i][k:], p1[i][:k]])
+
+    def MultByMonomial(self, p1, k, p2):                        # ring/operations.go:306-363
+        N = self.N()
+        shift = (k + (N << 1)) % (N << 1)
+        if shift == 0:
+            p2[: self.level + 1] = p1[: self.level + 1]
+            return
+        tmpx = np.zeros_like(p1)
+        for i, s in enumerate(self.SubRings[: self.level + 1]):
+            tmpx[i] = p1[i] if shift < N else (np.uint64(s.Modulus) - p1[i])
+        shift %= N
+        for i, s in enumerate(self.SubRings[: self.level + 1]):
+            out = np.empty(N, dtype=U64)
+            out[:shift] = np.uint64(s.Modulus) - tmpx[i][N - shift:]
+            out[shift:] = tmpx[i][: N - shift]
+            p2[i] = out
+
+    def MulByVectorMontgomery(self, p1, vector, p2):            # ring/operations.go:366-370
+        for i, s in enumerate(self.SubRings[: self.level + 1]): s.vecop("MulCoeffsMontgomery", p1[i], vector, p2[i])
+
+    def MulByVectorMontgomeryThenAddLazy(self, p1, vector, p2):  # ring/operations.go:373-377
+        for i, s in enumerate(self.SubRings[: self.level + 1]): s.vecop("MulCoeffsMontgomeryThenAddLazy", p1[i], vector, p2[i])
+
     def NTT(self, p1, p2):        # ring/ntt.go:127
         for i, s in enumerate(self.SubRings[: self.level + 1]): s.NTT(p1[i], p2[i])
 
@@ -387,10 +458,10 @@ class Ring:
     def AutomorphismNTT(self, polIn, gen, polOut):                  # :38-45
         self.AutomorphismNTTWithIndex(polIn, self.AutomorphismNTTIndex(gen), polOut)
 
-    def Automorphism(self, polIn, gen, polOut):                     # :113-176 (Standard ring)
-        assert self.Type == "Standard"
+    def Automorphism(self, polIn, gen, polOut):                     # :113-176
+        f = lib().lo_automorphism_row if self.Type == "Standard" else lib().lo_automorphism_row_ci
         for i, s in enumerate(self.SubRings[: self.level + 1]):
-            lib().lo_automorphism_row(_ptr(polIn[i]), _ptr(polOut[i]), self.N(), gen, s.Modulus)
+            f(_ptr(polIn[i]), _ptr(polOut[i]), self.N(), gen, s.Modulus)
 
     # --- ring/scaling.go ---
     def DivFloorByLastModulusNTT(self, p0, p1):     # :6-22
@@ -502,6 +573,25 @@ class Ring:
 # --------------------------------------------------------------------------
 # ring/basis_extension.go
 # --------------------------------------------------------------------------
+def MapSmallDimensionToLargerDimensionNTT(polSmall, polLarge):      # ring/operations.go:380-392
+    gap = polLarge.shape[1] // polSmall.shape[1]
+    for j in range(min(polSmall.shape[0], polLarge.shape[0])):
+        polLarge[j] = np.repeat(polSmall[j], gap)
+
+
+def ExtendBasisSmallNormAndCenter(ringQ: "Ring", ringP: "Ring", polyInQ, levelP, polyOutQ, polyOutP):
+    """ringqp.Ring.ExtendBasisSmallNormAndCenter, ring/ringqp/operations.go:325-351."""
+    Q = ringQ.SubRings[0].Modulus
+    QHalf = Q >> 1
+    if polyOutQ is not polyInQ:
+        polyOutQ[...] = polyInQ
+    c = polyInQ[0].copy()
+    negm = c > np.uint64(QHalf)
+    mag = np.where(negm, np.uint64(Q) - c, c)
+    for i, pi in enumerate(ringP.ModuliChain()[: levelP + 1]):
+        polyOutP[i] = np.where(negm, np.uint64(pi) - mag, mag)
+
+
 class ModUpConstants:
     """GenModUpConstants, ring/basis_extension.go:101-172 (big-int restatement)."""
 
@@ -952,6 +1042,22 @@ class Evaluator:
         index = ringQ.AutomorphismNTTIndex(galEl)
         ringQ.AutomorphismNTTWithIndex(tmp[0], index, ctOut[0])
         ringQ.AutomorphismNTTWithIndex(tmp[1], index, ctOut[1])
+
+    # core/rlwe/evaluator_automorphism.go:107-165 (ctQP.IsNTT branch): result modulo QP, scaled by P.
+    # ctQP = ([Q0, Q1], [P0, P1]) pre-allocated (levelQ+1 / levelP+1 rows).
+    def AutomorphismHoistedLazy(self, levelQ, ctIn, decompQ, decompP, galEl, evk: GadgetCiphertext, ctQP_Q, ctQP_P):
+        levelP = evk.LevelP()
+        ringQ = self.params.ringQ.AtLevel(levelQ); ringP = self.params.ringP.AtLevel(levelP)
+        N = ringQ.N()
+        tQ = [np.empty((levelQ + 1, N), dtype=U64) for _ in range(2)]
+        tP = [np.empty((levelP + 1, N), dtype=U64) for _ in range(2)]
+        self.GadgetProductHoistedLazy(levelQ, decompQ, decompP, evk, tQ, tP)
+        index = ringQ.AutomorphismNTTIndex(galEl)
+        ringQ.AutomorphismNTTWithIndex(tQ[1], index, ctQP_Q[1]); ringP.AutomorphismNTTWithIndex(tP[1], index, ctQP_P[1])
+        if levelP > -1:
+            ringQ.MulScalarBigint(ctIn[0], ringP.ModulusAtLevel[levelP], tQ[1])
+        ringQ.Add(tQ[0], tQ[1], tQ[0])
+        ringQ.AutomorphismNTTWithIndex(tQ[0], index, ctQP_Q[0]); ringP.AutomorphismNTTWithIndex(tP[0], index, ctQP_P[0])
 
     # core/rlwe/evaluator_evaluationkey.go:121-148
     def Relinearize(self, ctIn, rlk: GadgetCiphertext, opOut):
