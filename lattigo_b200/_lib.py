@@ -6,7 +6,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "lib", "liblattigo_b200.so")
+# LGPU_SO_PATH: development override used to A/B kernel variants built into lib/variants/ (never a CPU path)
+SO_PATH = os.environ.get("LGPU_SO_PATH") or os.path.join(HERE, "lib", "liblattigo_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "lattigo_b200.h")
 
 _lib = None

@@ -140,16 +140,12 @@ struct KsStridedParams {
 // ext value of one coefficient for target limb (q, qinv): reference formula of multSum + centring, reduced to < 3q.
 template <int NSMAX>
 __device__ __forceinline__ u64 ks_ext(const u64 (&y)[NSMAX], int nS, int v, const u64* c, const u64* vt, u64 half_t, u64 q, u64 qinv) {
-    u64 rhi = 0, rlo = 0;
+    // 128-bit accumulation through one __int128 so that the partial products chain on IMAD.WIDE / IADD3.X carries
+    unsigned __int128 acc = 0;
 #pragma unroll
-    for (int i = 0; i < NSMAX; i++) {
-        if (i < nS) {
-            u64 mhi, mlo;
-            mul128(y[i], c[i], mhi, mlo);
-            rlo += mlo;
-            rhi += mhi + (rlo < mlo);
-        }
-    }
+    for (int i = 0; i < NSMAX; i++)
+        if (i < nS) acc += (unsigned __int128)y[i] * c[i];
+    const u64 rlo = (u64)acc, rhi = (u64)(acc >> 64);
     const u64 hhi = mulhi64(rlo * qinv, q);
     u64 r = rhi - hhi + q + vt[v];
     return cred(r + q - half_t, q);
@@ -157,7 +153,7 @@ __device__ __forceinline__ u64 ks_ext(const u64 (&y)[NSMAX], int nS, int v, cons
 
 enum { PRO_MODUP = 0, PRO_BCAST = 1 };
 #ifndef KS_STRIDED_MINB
-#define KS_STRIDED_MINB 4
+#define KS_STRIDED_MINB 5
 #endif
 
 template <int RL, int NSMAX, bool FP, int PRO>
