@@ -11,6 +11,10 @@
  *   - Polynomials are `uint64_t*` DEVICE-ACCESSIBLE pointers (cudaMalloc / managed / lgpu_malloc) to a
  *     contiguous (limb, coeff) row-major block: row i = residues mod the i-th modulus, N words per row.
  *     ring.Poly{Coeffs [][]uint64} (ring/poly.go:13-15) maps onto it with Coeffs[i] = row i.
+ *   - Alignment: lgpu_malloc / cudaMalloc blocks are always fine. The ring-level entry points accept any
+ *     8-byte aligned pointer (odd word offsets take 64-bit kernels); the rlwe-level ones (gadget products,
+ *     evaluator_*, ckks_*) and evaluation keys require 16-byte aligned blocks and even strides, and return
+ *     an error otherwise (their kernels move 128 bits per access).
  *   - `ring` selects the moduli chain: LGPU_RING_Q or LGPU_RING_P (ringqp.Ring{RingQ,RingP},
  *     ring/ringqp/ring.go:15-17). `level` is the reference's level (number of limbs - 1).
  *   - All calls are asynchronous on `stream` (a cudaStream_t cast to void*; NULL = the CUDA default

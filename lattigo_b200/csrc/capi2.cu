@@ -18,12 +18,16 @@ struct lgpu_ctx {
             return -1;                     \
         }                                  \
     } while (0)
+// the key-switch family moves 128 bits per access: polynomial blocks must be 16-byte aligned with even strides
+#define AL(p) ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)
+#define REQUIRE_ALIGNED(cond) REQUIRE(cond, "polynomial buffers and evaluation keys must be 16-byte aligned with even strides (words)")
 #define REQUIRE_DEVICE(ctx) REQUIRE((ctx) && (ctx)->c.device >= 0, "this context was created host-only (device < 0): no device execution")
 
 static inline cudaStream_t S(void* stream) { return (cudaStream_t)stream; }
 
 static int to_gct(const lgpu_gadget_ct* e, GadgetCt& g) {
     REQUIRE(e && e->data, "null evaluation key");
+    REQUIRE_ALIGNED(AL(e->data));
     g.data = (const u64*)e->data; g.levelQ = e->level_q; g.levelP = e->level_p; g.pw2 = e->base_two_decomposition;
     g.ndigits = e->n_digits; g.npw2max = e->n_pw2_max > 0 ? e->n_pw2_max : 1; g.pw2_sizes = e->pw2_sizes;
     return 0;
@@ -137,6 +141,7 @@ int lgpu_gadget_product(lgpu_ctx* ctx, int lq, const uint64_t* cx, const lgpu_ga
                         size_t scx, size_t sct, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(cx && ct0 && ct1, "null polynomial");
+    REQUIRE_ALIGNED(AL(cx) && AL(ct0) && AL(ct1) && ((scx | sct) & 1) == 0);
     GadgetCt g;
     if (to_gct(evk, g)) return -1;
     lq = std::min(lq, g.levelQ);   // core/rlwe/evaluator_gadget_product.go:18
@@ -147,6 +152,7 @@ int lgpu_gadget_product_lazy(lgpu_ctx* ctx, int lq, const uint64_t* cx, const lg
                              uint64_t* a1p, int batch, size_t scx, size_t sq, size_t sp, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(cx && a0q && a1q, "null polynomial");
+    REQUIRE_ALIGNED(AL(cx) && AL(a0q) && AL(a0p) && AL(a1q) && AL(a1p) && ((scx | sq | sp) & 1) == 0);
     GadgetCt g;
     if (to_gct(evk, g)) return -1;
     REQUIRE(g.levelP < 0 || (a0p && a1p), "null P accumulator");
@@ -157,6 +163,7 @@ int lgpu_evaluator_moddown(lgpu_ctx* ctx, int lq, int lp, const uint64_t* a0q, c
                            uint64_t* ct0, uint64_t* ct1, int batch, size_t sq, size_t sp, size_t sct, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(a0q && a1q && ct0 && ct1, "null polynomial");
+    REQUIRE_ALIGNED(AL(a0q) && AL(a0p) && AL(a1q) && AL(a1p) && AL(ct0) && AL(ct1) && ((sq | sp | sct) & 1) == 0);
     if (check_levels(ctx->c, lq, lp, lp >= 0)) return -1;
     const size_t N = ctx->c.N;
     return evaluator_moddown_ntt(&ctx->c, lq, lp, make_acc((u64*)a0q, (u64*)a0p, (u64*)a1q, (u64*)a1p, N, sq, sp), Span{(u64*)ct0, N, sct},
@@ -181,6 +188,7 @@ int lgpu_gadget_product_hoisted(lgpu_ctx* ctx, int lq, const uint64_t* decomp, c
                                 size_t sct, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(decomp && ct0 && ct1, "null polynomial");
+    REQUIRE_ALIGNED(AL(decomp) && AL(ct0) && AL(ct1) && (sct & 1) == 0);
     GadgetCt g;
     if (to_gct(evk, g)) return -1;
     const size_t N = ctx->c.N;
@@ -190,6 +198,7 @@ int lgpu_gadget_product_hoisted_lazy(lgpu_ctx* ctx, int lq, const uint64_t* deco
                                      uint64_t* a1q, uint64_t* a1p, int batch, size_t sq, size_t sp, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(decomp && a0q && a0p && a1q && a1p, "null polynomial");
+    REQUIRE_ALIGNED(AL(decomp) && AL(a0q) && AL(a0p) && AL(a1q) && AL(a1p) && ((sq | sp) & 1) == 0);
     GadgetCt g;
     if (to_gct(evk, g)) return -1;
     const size_t N = ctx->c.N;
@@ -199,6 +208,7 @@ int lgpu_evaluator_automorphism(lgpu_ctx* ctx, int level, const uint64_t* ct_in,
                                 uint64_t* ct_out, int batch, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(ct_in && ct_out, "null ciphertext");
+    REQUIRE_ALIGNED(AL(ct_in) && AL(ct_out));
     GadgetCt g;
     if (to_gct(gk, g)) return -1;
     REQUIRE(level >= 0 && level <= g.levelQ && level < ctx->c.nQ, "level out of range");
@@ -211,6 +221,7 @@ int lgpu_evaluator_automorphism(lgpu_ctx* ctx, int level, const uint64_t* ct_in,
 int lgpu_evaluator_relinearize(lgpu_ctx* ctx, int level, const uint64_t* ct_in, const lgpu_gadget_ct* rlk, uint64_t* ct_out, int batch, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(ct_in && ct_out, "null ciphertext");
+    REQUIRE_ALIGNED(AL(ct_in) && AL(ct_out));
     GadgetCt g;
     if (to_gct(rlk, g)) return -1;
     REQUIRE(level >= 0 && level <= g.levelQ && level < ctx->c.nQ, "level out of range");
@@ -225,6 +236,7 @@ int lgpu_ckks_mulrelin_rescale_batch(lgpu_ctx* ctx, int level, const uint64_t* c
                                      uint64_t* ct_out, int batch, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(ct_a && ct_b && ct_out, "null ciphertext");
+    REQUIRE_ALIGNED(AL(ct_a) && AL(ct_b) && AL(ct_out));
     REQUIRE(batch >= 1, "batch must be >= 1");
     GadgetCt g;
     if (to_gct(rlk, g)) return -1;

@@ -101,6 +101,11 @@ struct Ctx {
     std::vector<std::pair<u64, unsigned int*>> auto_index;
 };
 
+// 128-bit vector accesses need 16-byte aligned bases and even strides (in words); callers that hand in odd row offsets
+// are routed to the 64-bit kernels instead.
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool even_words(size_t a, size_t b = 0, size_t c = 0) { return ((a | b | c) & 1u) == 0; }
+
 // ---- error handling --------------------------------------------------------------------------------
 void set_error(const std::string& msg);
 const char* last_error();

@@ -580,6 +580,172 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8_kernel(KsChunkParams 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K3, register-MAC variant of the 512 x 8 kernel. The last radix-8 round leaves every thread with 8 CONSECUTIVE
+// coefficients in registers (stages 9..11 act inside aligned groups of 8), so the MAC consumes them right there:
+//   * no store / barrier / reload of the transformed tile before the MAC,
+//   * key rows, own rows and results move as 128-bit accesses (64 contiguous bytes per thread),
+//   * the accumulators of those 8 coefficients are private to the thread (shared memory is only their spill space,
+//     laid out so that 128-bit accesses are conflict-free), hence the MAC phase has no barrier at all,
+//   * the only ordering the next digit needs -- "everybody has read the tile before I overwrite it" -- is a split
+//     mbarrier: arrive right after the last-round reads, wait just before the next digit's first-round stores.
+// Warps therefore drift apart inside a CTA and the integer MAC of one warp overlaps the FP64 butterflies of another.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u64 mbar_arrive(unsigned bar) {
+    u64 tok;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(tok) : "r"(bar) : "memory");
+    return tok;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, u64 tok) {
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "l"(tok) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ ulonglong2 ldg128(const u64* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
+
+template <int PREF>
+__global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams p) {
+    constexpr int CL = 12, T = 512;
+    extern __shared__ u64 smem[];
+    __shared__ __align__(8) u64 s_bar;
+    double* fsm = reinterpret_cast<double*>(smem);
+    // accumulators: component c, pair j (coefficients 8*tid + 2j, 2j+1) at acc + ((c*4 + j) * T + tid) * 2
+    ulonglong2* accs = reinterpret_cast<ulonglong2*>(smem + 4096 + 256 + 8);
+    const int b = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+    const int limb = p.rm.limb[blockIdx.z];
+    const int row = p.rm.drow[blockIdx.z];
+    const LimbConst L = p.limbs[limb];
+    const int s1 = p.logN - CL;
+    const int N = 1 << p.logN;
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
+    const double fq = L.fq, fqinv = L.fqinv;
+    const double* tw = L.ftw_fwd;
+    const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
+    const u64* P1row = p.P1 + (size_t)b * p.p1_bs + (size_t)row * N + ((size_t)chunk << CL);
+    const u64* xin = p.cx + (size_t)b * p.cx_bs + (size_t)row * p.cx_rs + ((size_t)chunk << CL) + 8 * tid;
+    const int own_d = row < p.nq ? row / p.k : -1;
+    const unsigned bar = smem_addr(&s_bar);
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(T) : "memory");
+    __syncthreads();
+    u64 raw[8];
+    if (PREF) {
+        const int d0 = own_d == 0 ? 1 : 0;
+        if (d0 < p.nd) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d0 * p.p1_ds + k * T + tid];
+        }
+    }
+    u64 tok = 0;
+    bool pending = false;      // a tile read phase is outstanding: wait for it before overwriting the tile
+    for (int d = 0; d < p.nd; d++) {
+        const bool own = d == own_d;
+        const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow + 8 * tid;
+        const u64* e1 = e0 + p.evk_cs;
+        int dn = d + 1;
+        if (dn == own_d) dn++;
+        u64 xv[8];
+        if (!own) {
+            {
+                double x[8];
+                if (!PREF) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d * p.p1_ds + k * T + tid];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)raw[k]);
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int half = 4 >> u;
+                    const int twbase = (1 << (s1 + u)) + (chunk << u);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (k & half) continue;
+                        fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), fq, fqinv);
+                    }
+                }
+                if (pending) { mbar_wait(bar, tok); pending = false; }
+#pragma unroll
+                for (int k = 0; k < 8; k++) fsm[fpad(k * T + tid)] = x[k];
+            }
+            double t[7];
+            fp8_load_tw<3>(t, tw, s1, chunk, tid);
+            __syncthreads();
+            fp8_round<3>(fsm, t, fq, fqinv, tid);
+            fp8_load_tw<6>(t, tw, s1, chunk, tid);
+            __syncthreads();
+            fp8_round<6>(fsm, t, fq, fqinv, tid);
+            fp8_load_tw<9>(t, tw, s1, chunk, tid);
+            __syncthreads();
+            {   // last round stays in registers: coefficients 8*tid .. 8*tid+7
+                double x[8];
+                const int base = tid << 3;
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = fsm[fpad(base + k)];
+                tok = mbar_arrive(bar);
+                pending = true;
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int half = 4 >> u;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (k & half) continue;
+                        fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], fq, fqinv);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) xv[k] = fp_canon(x[k], fq, fqinv);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const ulonglong2 v = ldg128(xin + 2 * j); xv[2 * j] = v.x; xv[2 * j + 1] = v.y; }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            ulonglong2 k0[2], k1[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) { k0[j] = ldg128(e0 + 4 * h + 2 * j); k1[j] = ldg128(e1 + 4 * h + 2 * j); }
+            if (PREF && h == 1 && !own && dn < p.nd) {
+                // next digit's tile: issued here so that the loads fly during the second MAC half and the barrier wait
+#pragma unroll
+                for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int pj = 2 * h + j;
+                const u64 xa = xv[2 * pj], xb = xv[2 * pj + 1];
+                ulonglong2 m0, m1;
+                m0.x = mred_lazy(k0[j].x, xa, q, qinv); m0.y = mred_lazy(k0[j].y, xb, q, qinv);
+                m1.x = mred_lazy(k1[j].x, xa, q, qinv); m1.y = mred_lazy(k1[j].y, xb, q, qinv);
+                ulonglong2* A0 = accs + (size_t)(0 * 4 + pj) * T + tid;
+                ulonglong2* A1 = accs + (size_t)(1 * 4 + pj) * T + tid;
+                if (d != 0) {
+                    const ulonglong2 c0 = *A0, c1 = *A1;
+                    u64 v;
+                    v = c0.x + m0.x; m0.x = v >= twoq ? v - twoq : v;
+                    v = c0.y + m0.y; m0.y = v >= twoq ? v - twoq : v;
+                    v = c1.x + m1.x; m1.x = v >= twoq ? v - twoq : v;
+                    v = c1.y + m1.y; m1.y = v >= twoq ? v - twoq : v;
+                }
+                *A0 = m0; *A1 = m1;
+            }
+        }
+    }
+    u64* o0 = p.acc + (size_t)b * p.acc_bs + (size_t)row * N + ((size_t)chunk << CL) + 8 * tid;
+    u64* o1 = o0 + p.acc_cs;
+#pragma unroll
+    for (int pj = 0; pj < 4; pj++) {
+        const ulonglong2 c0 = accs[(size_t)(0 * 4 + pj) * T + tid], c1 = accs[(size_t)(1 * 4 + pj) * T + tid];
+        ulonglong2 r0, r1;
+        r0.x = cred(c0.x >= twoq ? c0.x - twoq : c0.x, q); r0.y = cred(c0.y >= twoq ? c0.y - twoq : c0.y, q);
+        r1.x = cred(c1.x >= twoq ? c1.x - twoq : c1.x, q); r1.y = cred(c1.y >= twoq ? c1.y - twoq : c1.y, q);
+        *reinterpret_cast<ulonglong2*>(o0 + 2 * pj) = r0;
+        *reinterpret_cast<ulonglong2*>(o1 + 2 * pj) = r1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------------------
 bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
@@ -707,8 +873,17 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         }
         // algorithmic bytes: P1 read once + accumulators written once + evk once per launch
         ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * fp.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
-        static const int k3v = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 8; }();
-        if (k3v == 8) {
+        static const int k3v_env = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 10; }();
+        const bool vec_ok = aligned16(cp.evk) && aligned16(cp.cx) && aligned16(cp.acc) && even_words(cp.evk_ds, cp.evk_cs) &&
+                            even_words(cp.cx_rs, cp.cx_bs) && even_words(cp.acc_cs, cp.acc_bs);
+        const int k3v = (k3v_env >= 9 && !vec_ok) ? 8 : k3v_env;
+        if (k3v == 9) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8r_kernel<1><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        } else if (k3v == 10) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8r_kernel<0><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        } else if (k3v == 8) {
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ks_chunk_mac_fp8_kernel<<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
         } else {
@@ -847,22 +1022,37 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
     __syncthreads();
     fp8_round<6>(fsm, t, fq, fqinv, tid);
     fp8_load_tw<9>(t, tw, s1, chunk, tid);
-    __syncthreads();
-    fp8_round<9>(fsm, t, fq, fqinv, tid);
-    u64 a[8], d[8];
+    // the operands of the epilogue for this thread's 8 consecutive coefficients (last round: stages 9..11 act inside
+    // aligned groups of 8), issued before the barrier so that their latency overlaps the wait
+    ulonglong2 a[4], d[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        a[j] = A[j * T + tid];
-        d[j] = D ? D[j * T + tid] : 0;
+    for (int j = 0; j < 4; j++) {
+        a[j] = *reinterpret_cast<const ulonglong2*>(A + 8 * tid + 2 * j);
+        d[j] = D ? *reinterpret_cast<const ulonglong2*>(D + 8 * tid + 2 * j) : make_ulonglong2(0, 0);
     }
     __syncthreads();
+    double x[8];
+    {
+        const int base = tid << 3;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int idx = j * T + tid;
-        const u64 x = fp_canon(fsm[fpad(idx)], fq, fqinv);
-        u64 r = mred(x + twoq - a[j], sc, q, qinv);
-        if (D) r = cred(r + d[j], q);
-        out[idx] = r;
+        for (int k = 0; k < 8; k++) x[k] = fsm[fpad(base + k)];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int half = 4 >> u;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k & half) continue;
+                fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], fq, fqinv);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        ulonglong2 r;
+        r.x = mred(fp_canon(x[2 * j], fq, fqinv) + twoq - a[j].x, sc, q, qinv);
+        r.y = mred(fp_canon(x[2 * j + 1], fq, fqinv) + twoq - a[j].y, sc, q, qinv);
+        if (D) { r.x = cred(r.x + d[j].x, q); r.y = cred(r.y + d[j].y, q); }
+        *reinterpret_cast<ulonglong2*>(out + 8 * tid + 2 * j) = r;
     }
 }
 
@@ -870,7 +1060,9 @@ template <bool FP>
 static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
     const size_t smem = (size_t)(4096 + 256 + 8) * sizeof(u64);
     static const int v8 = [] { const char* e = getenv("LGPU_FZ_VARIANT"); return e ? atoi(e) : 8; }();
-    if (FP && v8 == 8) {
+    const bool vec_ok = aligned16(p.A) && aligned16(p.D) && aligned16(p.out) && even_words(p.a_cs, p.a_bs) && even_words(p.d_cs, p.d_bs) &&
+                        even_words(p.o_cs, p.o_bs);
+    if (FP && v8 == 8 && vec_ok) {
         fz_chunk_epi_fp8_kernel<<<grid, 512, smem, st>>>(p);
         LGPU_CUDA_OK(cudaGetLastError());
         return 0;

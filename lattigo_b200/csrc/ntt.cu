@@ -378,7 +378,9 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     if (check_common(c, rm, batch)) return -1;
     if (c->ring_type != 0) return launch_ntt_ci(c, rm, false, in, out, batch, mode == NTT_EXACT_LAZY, st);
     RowMap fp, rest;
-    if (mode == NTT_CANONICAL && split_rows_fp64(c, rm, fp, rest)) {
+    // the FP64 forward chunk pass stores 128 bits at a time
+    const bool vec_ok = aligned16(out.p) && even_words(out.row_stride, out.batch_stride);
+    if (mode == NTT_CANONICAL && vec_ok && split_rows_fp64(c, rm, fp, rest)) {
         {
             ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * fp.nrows * batch, c->logN > 12 ? 2 : 1);
             if (launch_ntt_fp64(c, fp, false, in, out, batch, st)) return -1;

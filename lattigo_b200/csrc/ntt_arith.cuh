@@ -245,5 +245,32 @@ __device__ __forceinline__ void fp_fwd_round_tw(double* sm, const double (&t)[15
     }
 }
 
+// Last forward round (A + RB == CL): every group is 2^RB CONSECUTIVE coefficients, so the canonical results go straight
+// from registers to global memory as 128-bit stores (no store / barrier / reload of the tile for a coalesced copy-out).
+template <int CL, int A, int RB>
+__device__ __forceinline__ void fp_fwd_round_tw_out(const double* sm, const double (&t)[15], double q, double qinv, int tid, u64* gdst) {
+    static_assert(A + RB == CL && RB >= 1, "last round only");
+    constexpr int G = 16 >> RB, RR = 1 << RB;
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int base = (tid * G + gi) << RB;
+        double x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) x[k] = sm[fpad(base + k)];
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int half = 1 << (RB - 1 - u);
+#pragma unroll
+            for (int k = 0; k < RR; k++) {
+                if (k & half) continue;
+                fp_fwd_bfly(x[k], x[k + half], t[gi * (RR - 1) + (1 << u) - 1 + (k >> (RB - u))], q, qinv);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k += 2)
+            *reinterpret_cast<ulonglong2*>(gdst + base + k) = make_ulonglong2(fp_canon(x[k], q, qinv), fp_canon(x[k + 1], q, qinv));
+    }
+}
+
 
 }  // namespace lgpu

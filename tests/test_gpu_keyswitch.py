@@ -433,3 +433,51 @@ def test_bgv_rotate_full_size_n15qp880():
         ev_o.Automorphism([cth[i, 0], cth[i, 1]], galEl, gk_o, w)
         assert np.array_equal(oh[i, 0], w[0]) and np.array_equal(oh[i, 1], w[1]), i
     ctx.close()
+
+
+def test_unaligned_buffers():
+    """Polynomials at an odd word offset (8- but not 16-byte aligned): ring-level calls route them to the 64-bit
+    kernels and stay bit-exact; the rlwe-level calls (128-bit accesses) refuse them with an error, as the header says."""
+    import torch
+    lb = _lb()
+    logN = 13
+    q, p = _mods(logN, [56, 45, 45, 45], [55, 55])
+    ctx = lb.Context(logN, q, p)
+    params = O.Parameters(logN, q, p)
+    N = params.N()
+    rng = np.random.default_rng(71)
+    level = 3
+
+    def odd(arr):
+        flat = torch.zeros(arr.size + 1, dtype=torch.int64, device="cuda")
+        view = flat[1:].view(*arr.shape)
+        view.copy_(ctx.to_device(arr))
+        assert view.data_ptr() % 16 == 8
+        return view
+
+    x = H.rand_poly(q, N, rng)
+    ring = O.Ring(N, q)
+    want = np.empty_like(x); want_i = np.empty_like(x); want_m = np.empty_like(x)
+    ring.NTT(x, want); ring.INTT(x, want_i); ring.MulCoeffsMontgomery(x, x, want_m)
+    dx = odd(x); out = odd(np.zeros_like(x))
+    ctx.ringQ.NTT(dx, out)
+    assert np.array_equal(ctx.to_host(out), want)
+    ctx.ringQ.INTT(dx, out)
+    assert np.array_equal(ctx.to_host(out), want_i)
+    ctx.ringQ.MulCoeffsMontgomery(dx, dx, out)
+    assert np.array_equal(ctx.to_host(out), want_m)
+    rlk_o = H.random_gadget_ciphertext(params, level, params.MaxLevelP(), rng)
+    rlk = lb.GadgetCiphertext(ctx, rlk_o.data, rlk_o.LevelQ(), rlk_o.LevelP())
+    cx = H.rand_poly(q, N, rng)
+    c0 = ctx.ringQ.NewPoly(); c1 = ctx.ringQ.NewPoly()
+    with pytest.raises(lb.LgpuError, match="16-byte aligned"):
+        lb.Evaluator(ctx).GadgetProduct(level, odd(cx), rlk, c0, c1)
+    with pytest.raises(lb.LgpuError, match="16-byte aligned"):
+        lb.Evaluator(ctx).GadgetProduct(level, ctx.to_device(cx), rlk, odd(np.zeros_like(cx)), c1)
+    bad = lb.GadgetCiphertext(ctx, odd(rlk_o.data), rlk_o.LevelQ(), rlk_o.LevelP())
+    with pytest.raises(lb.LgpuError, match="16-byte aligned"):
+        lb.Evaluator(ctx).GadgetProduct(level, ctx.to_device(cx), bad, c0, c1)
+    a = np.stack([H.rand_poly(q, N, rng) for _ in range(2)])[None]
+    with pytest.raises(lb.LgpuError, match="16-byte aligned"):
+        lb.CKKSEvaluator(ctx, rlk).MulRelinRescaleNew(odd(a), ctx.to_device(a))
+    ctx.close()
