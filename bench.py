@@ -279,7 +279,7 @@ def gpu_main(args):
         # dominant kernel class of the step (by summed CUDA-event time of its launch scopes)
         dom = max(range(nk), key=lambda i: ms[i])
         kernel_names = {
-            "mac": "ks_chunk_mac_kernel (fused: chunk-pass NTT, 12 stages, + key-switch MAC over all digits; accumulators in smem)",
+            "mac": "ks_chunk_mac_fp8r_kernel (K3: chunk-pass NTT, 12 stages on the FP64 pipe, + key-switch MAC over all digits from registers)",
             "fused": "ks_strided_kernel / fz_chunk_epi_kernel (basis extension folded into the strided NTT pass; ModDown / rescale epilogues)",
             "ntt_fwd": "ntt strided + chunk pass kernels (forward)", "ntt_inv": "ntt chunk + strided pass kernels (inverse)",
             "modup": "ks_prepare_kernel / modup_kernel", "vecop": "vecop_kernel", "tensor": "ckks_tensor_kernel",
@@ -316,8 +316,9 @@ def gpu_main(args):
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
                 "traffic": traffic, "avg_launch_ms": ms[dom] / max(1, int(sc[dom])), "alg_bytes_per_launch": by[dom] / max(1, int(sc[dom])),
                 "share_of_step": ms[dom] / tot, "ntt_standalone": ntt_standalone, "classes": classes,
-                "note": "classes: summed CUDA-event time of launch scopes on their launching streams over the same K steps; "
-                        "integer-row chains run on a side stream concurrently with the FP64-row chains, so class times may overlap"}
+                "note": "classes: summed CUDA-event time of launch scopes over the same K steps re-run with the event profiler on; "
+                        "in that re-run the integer-row chains stay on the main stream (normally a side stream), so class times do "
+                        "not overlap and add up to the step"}
     barrier()
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region) ------

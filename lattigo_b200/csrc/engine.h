@@ -164,6 +164,7 @@ int launch_modup_qp(const Ctx* c, bool toP, int levelQ, int levelP, CSpan in, Sp
 int launch_decompose_and_split(const Ctx* c, int levelQ, int levelP, int nbPi, int digit, CSpan p0Q, Span p1Q, Span p1P,
                                int batch, cudaStream_t st);
 
+bool profiling_on();   // event profiler active: kernel chains are kept on ONE stream so that class times do not overlap
 // prof.cu: launch accounting + optional event profiling (kernel classes = LGPU_KCLASS_* of the public header)
 void count_launch(int n);
 class ProfScope {

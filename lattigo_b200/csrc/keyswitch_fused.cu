@@ -57,7 +57,7 @@ static int k2_fpsum() {
 }
 // returns the stream for the integer chain (forked from `st`), or `st` itself when side streams are unavailable
 static cudaStream_t fork_side(const Ctx* c, cudaStream_t st, bool have_both) {
-    if (!have_both) return st;
+    if (!have_both || profiling_on()) return st;
     SideStream* ss = side_stream(c->device);
     if (!ss) return st;
     cudaEventRecord(ss->fork, st);

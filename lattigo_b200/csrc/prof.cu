@@ -15,6 +15,7 @@ struct ProfRec { int k; cudaEvent_t a, b; double bytes; int kernels; };
 static std::mutex g_mu;
 static std::vector<ProfRec> g_recs;
 
+bool profiling_on() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 ProfScope::ProfScope(int k, cudaStream_t st, double bytes, int kernels) : k_(k), st_(st), on_(false), bytes_(bytes), kernels_(kernels) {
