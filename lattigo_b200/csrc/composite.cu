@@ -685,8 +685,8 @@ static int ckks_mulrelin_rescale_chunk(const Ctx* c, int level, const u64* ctA, 
 static int batch_chunk() {
     static int v = [] {
         const char* e = getenv("LGPU_BATCH_CHUNK");
-        int x = e ? atoi(e) : 16;
-        return x > 0 ? x : 16;
+        int x = e ? atoi(e) : 32;
+        return x > 0 ? x : 32;
     }();
     return v;
 }

@@ -155,6 +155,12 @@ enum { PRO_MODUP = 0, PRO_BCAST = 1 };
 #ifndef KS_STRIDED_MINB
 #define KS_STRIDED_MINB 5
 #endif
+#ifndef KS_STRIDED_J4_MINB
+#define KS_STRIDED_J4_MINB 4
+#endif
+#ifndef KS_J
+#define KS_J 8   // target rows sharing one staged y/v tile
+#endif
 
 template <int RL, int NSMAX, bool FP, int PRO>
 __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStridedParams p) {
@@ -175,8 +181,15 @@ __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStri
         if (threadIdx.x <= nS) s_vt[threadIdx.x] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + threadIdx.x];
     }
     __syncthreads();
+    // the strided pass always covers logN - 12 = RL stages, so N and the element stride are compile-time constants:
+    // every load/store below addresses base + immediate (no per-access address arithmetic on the ALU pipe)
+#ifdef KS_RUNTIME_STRIDE
     const int N = 1 << p.logN;
     const int stride = N >> RL;
+#else
+    constexpr int N = 4096 << RL;
+    constexpr int stride = 4096;
+#endif
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= stride) return;
     const u64 q = L.q, qinv = L.qinv;
@@ -281,6 +294,97 @@ __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStri
         }
 #pragma unroll
         for (int k = 0; k < R; k++) out[(size_t)k * stride + l] = e[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2, row-sharing variant. The plain kernel reads the digit's y_i (nS x 8 B) + v (1 B) once per TARGET ROW, i.e.
+// ~33 B from L2 per 8 B written: 73 GB of L2->SM traffic per 64-ciphertext step at L=44, which is what bounds it.
+// Here a CTA owns 64 strided columns (l) x all R strided coefficients and stages that y/v tile in shared memory once
+// for J = 4 target rows (thread = (column, target row)): L2 traffic drops 4x, the y reads become conflict-free /
+// broadcast shared-memory loads. Multi-source digits only (the single-limb rule keeps the plain kernel).
+// ------------------------------------------------------------------------------------------------------------
+template <int RL, int NSMAX, bool FP>
+__global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(KsStridedParams p) {
+    constexpr int R = 1 << RL, J = KS_J, LB = 256 / J;
+    extern __shared__ u64 dsm[];
+    u64* s_y = dsm;                                                        // [NSMAX][R][LB]
+    unsigned char* s_v = reinterpret_cast<unsigned char*>(dsm + NSMAX * R * LB);   // [R][LB]
+    __shared__ u64 s_c[J][NSMAX];
+    __shared__ u64 s_vt[J][NSMAX + 1];
+    const int tid = threadIdx.x, lx = tid % LB, jj = tid / LB;
+    const int jrow = blockIdx.y * J + jj;
+    const bool valid = jrow < p.rm.nrows;
+    const int limb = valid ? p.rm.limb[jrow] : 0;
+    const int row = valid ? p.rm.drow[jrow] : 0;
+    const int d = blockIdx.z % p.nd, b = blockIdx.z / p.nd;
+    const KsDigit dg = p.dg[d];
+    const int r0 = d * p.k;
+    const int nS = dg.nS;
+    constexpr int N = 4096 << RL;
+    constexpr int stride = 4096;
+    const int l0 = blockIdx.x * LB;
+    const u64* Y = p.Y + (size_t)b * p.y_bs + (size_t)r0 * N;
+    const unsigned char* V = p.V + (size_t)b * p.v_bs + (size_t)d * N;
+    for (int idx = tid; idx < nS * R * LB; idx += 256) {
+        const int i = idx / (R * LB), k = (idx / LB) % R, x = idx % LB;
+        s_y[idx] = Y[(size_t)i * N + k * stride + l0 + x];
+    }
+    for (int idx = tid; idx < R * LB / 4; idx += 256) {      // 4 bytes per thread: 16-column groups are 4-byte aligned
+        const int k = (idx * 4) / LB, x = (idx * 4) % LB;
+        reinterpret_cast<unsigned int*>(s_v)[idx] = *reinterpret_cast<const unsigned int*>(V + k * stride + l0 + x);
+    }
+    if (valid) {
+        if (lx < nS) s_c[jj][lx] = p.blob[dg.off_c + (size_t)limb * dg.ldc + lx];
+        if (lx <= nS) s_vt[jj][lx] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + lx];
+    }
+    __syncthreads();
+    if (!valid) return;
+    if (p.skip_own && row < p.nq && row >= r0 && row < r0 + nS) return;   // own rows come from the NTT input
+    const LimbConst L = p.limbs[limb];
+    const u64 q = L.q, qinv = L.qinv;
+    const u64 half_t = p.blob[dg.off_half_t + limb];
+    const int l = l0 + lx;
+    u64* out = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N + l;
+    u64 e[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        u64 y[NSMAX];
+#pragma unroll
+        for (int i = 0; i < NSMAX; i++) y[i] = i < nS ? s_y[(i * R + k) * LB + lx] : 0;
+        e[k] = ks_ext<NSMAX>(y, nS, (int)s_v[k * LB + lx], s_c[jj], s_vt[jj], half_t, q, qinv);
+    }
+    if constexpr (FP) {
+        const double fq = L.fq, fqinv = L.fqinv;
+        const double* tw = L.ftw_fwd;
+        double x[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) x[k] = u2d(e[k]);
+#pragma unroll
+        for (int u = 0; u < RL; u++) {
+            const int half = 1 << (RL - 1 - u);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                fp_fwd_bfly(x[k], x[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), fq, fqinv);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) out[(size_t)k * stride] = (u64)__double_as_longlong(x[k]);
+    } else {
+        const ulonglong2* tw = L.tw_fwd;
+        const u64 nq = 0ull - q, twoq = q << 1;
+#pragma unroll
+        for (int u = 0; u < RL; u++) {
+            const int half = 1 << (RL - 1 - u);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                fast_fwd_bfly(e[k], e[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), nq, twoq, 0, false);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) out[(size_t)k * stride] = e[k];
     }
 }
 
@@ -761,8 +865,29 @@ bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
     return true;
 }
 
+template <int RL, int NSMAX, bool FP>
+static int ks_launch_j4(const KsStridedParams& p, dim3 grid, cudaStream_t st) {
+    constexpr int R = 1 << RL;
+    constexpr int LB = 256 / KS_J;
+    const size_t smem = (size_t)NSMAX * R * LB * sizeof(u64) + (size_t)R * LB;
+    LGPU_CUDA_OK(cudaFuncSetAttribute(ks_strided_j4_kernel<RL, NSMAX, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ks_strided_j4_kernel<RL, NSMAX, FP><<<dim3(grid.x * KS_J, (grid.y + KS_J - 1) / KS_J, grid.z), 256, smem, st>>>(p);
+    LGPU_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <bool FP, int PRO = PRO_MODUP>
 static int ks_launch_strided(int rl, int nsmax, const KsStridedParams& p, dim3 grid, cudaStream_t st) {
+    if constexpr (PRO == PRO_MODUP) {
+        static const int j4 = [] { const char* e = getenv("LGPU_K2_J4"); return e ? atoi(e) : 1; }();
+        bool multi = j4 != 0 && rl <= 4;                       // R = 32 (N = 2^17) would need 2 x 66 KB of shared memory
+        for (int d = 0; d < p.nd; d++) multi = multi && (p.dg[d].nS > 1 || !p.single_rule);
+        if (multi) {
+#define KS_J4(RLV) case RLV: return nsmax <= 4 ? ks_launch_j4<RLV, 4, FP>(p, grid, st) : ks_launch_j4<RLV, 8, FP>(p, grid, st);
+            switch (rl) { KS_J4(1) KS_J4(2) KS_J4(3) KS_J4(4) default: break; }
+#undef KS_J4
+        }
+    }
 #define KS_CASE(RLV) \
     case RLV: if (nsmax <= 4) ks_strided_kernel<RLV, 4, FP, PRO><<<grid, 256, 0, st>>>(p); else ks_strided_kernel<RLV, 8, FP, PRO><<<grid, 256, 0, st>>>(p); break;
     switch (rl) {
