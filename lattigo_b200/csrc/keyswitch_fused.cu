@@ -158,6 +158,12 @@ enum { PRO_MODUP = 0, PRO_BCAST = 1 };
 #ifndef KS_STRIDED_J4_MINB
 #define KS_STRIDED_J4_MINB 4
 #endif
+#ifndef KS_L2_PREFETCH_EVK
+#define KS_L2_PREFETCH_EVK 0
+#endif
+#ifndef KS_L2_PREFETCH
+#define KS_L2_PREFETCH 1
+#endif
 #ifndef KS_J
 #define KS_J 8   // target rows sharing one staged y/v tile
 #endif
@@ -756,6 +762,11 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                 if (!PREF) {
 #pragma unroll
                     for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d * p.p1_ds + k * T + tid];
+                    // pull the next digit's tile (32 KB = 256 lines) from HBM into L2 while this digit is processed
+                    if (KS_L2_PREFETCH && dn < p.nd && tid < 256)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P1row + (size_t)dn * p.p1_ds + tid * 16));
+                    if (KS_L2_PREFETCH_EVK && d + 1 < p.nd)   // next digit's key rows (both components), 256 lines each
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.evk + (size_t)(d + 1) * p.evk_ds + erow + (tid < 256 ? 0 : p.evk_cs) + (tid & 255) * 16));
                 }
 #pragma unroll
                 for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)raw[k]);
