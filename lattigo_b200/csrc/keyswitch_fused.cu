@@ -158,9 +158,6 @@ enum { PRO_MODUP = 0, PRO_BCAST = 1 };
 #ifndef KS_STRIDED_J4_MINB
 #define KS_STRIDED_J4_MINB 4
 #endif
-#ifndef KS_L2_PREFETCH_EVK
-#define KS_L2_PREFETCH_EVK 0
-#endif
 #ifndef KS_L2_PREFETCH
 #define KS_L2_PREFETCH 1
 #endif
@@ -590,105 +587,6 @@ __device__ __forceinline__ void fp8_round(double* sm, const double (&t)[7], doub
     for (int k = 0; k < 8; k++) sm[fpad(base + (k << LOB))] = x[k];
 }
 
-__global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8_kernel(KsChunkParams p) {
-    constexpr int CL = 12, T = 512;
-    extern __shared__ u64 smem[];
-    double* fsm = reinterpret_cast<double*>(smem);
-    u64* a0 = smem + 4096 + 256 + 8;
-    u64* a1 = a0 + 4096;
-    const int b = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
-    const int limb = p.rm.limb[blockIdx.z];
-    const int row = p.rm.drow[blockIdx.z];
-    const LimbConst L = p.limbs[limb];
-    const int s1 = p.logN - CL;
-    const int N = 1 << p.logN;
-    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
-    const double fq = L.fq, fqinv = L.fqinv;
-    const double* tw = L.ftw_fwd;
-    const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
-    const u64* P1row = p.P1 + (size_t)b * p.p1_bs + (size_t)row * N + ((size_t)chunk << CL);
-    const u64* xin = p.cx + (size_t)b * p.cx_bs + (size_t)row * p.cx_rs + ((size_t)chunk << CL);
-    const int own_d = row < p.nq ? row / p.k : -1;
-    u64 raw[8];
-    {
-        const int d0 = own_d == 0 ? 1 : 0;
-        if (d0 < p.nd) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d0 * p.p1_ds + k * T + tid];
-        }
-    }
-    for (int d = 0; d < p.nd; d++) {
-        const bool own = d == own_d;
-        const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow;
-        const u64* e1 = e0 + p.evk_cs;
-        int dn = d + 1;
-        if (dn == own_d) dn++;
-        if (!own) {
-            {
-                double x[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)raw[k]);
-#pragma unroll
-                for (int u = 0; u < 3; u++) {
-                    const int half = 4 >> u;
-                    const int twbase = (1 << (s1 + u)) + (chunk << u);
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        if (k & half) continue;
-                        fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), fq, fqinv);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; k++) fsm[fpad(k * T + tid)] = x[k];
-            }
-            double t[7];
-            fp8_load_tw<3>(t, tw, s1, chunk, tid);
-            __syncthreads();
-            fp8_round<3>(fsm, t, fq, fqinv, tid);
-            fp8_load_tw<6>(t, tw, s1, chunk, tid);
-            __syncthreads();
-            fp8_round<6>(fsm, t, fq, fqinv, tid);
-            fp8_load_tw<9>(t, tw, s1, chunk, tid);
-            __syncthreads();
-            fp8_round<9>(fsm, t, fq, fqinv, tid);
-            __syncthreads();
-            if (dn < p.nd) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            u64 k0[4], k1[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) { k0[j] = __ldg(e0 + (h * 4 + j) * T + tid); k1[j] = __ldg(e1 + (h * 4 + j) * T + tid); }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int idx = (h * 4 + j) * T + tid;
-                const u64 x = own ? xin[idx] : fp_canon(fsm[fpad(idx)], fq, fqinv);
-                const u64 m0 = mred_lazy(k0[j], x, q, qinv);
-                const u64 m1 = mred_lazy(k1[j], x, q, qinv);
-                if (d == 0) { a0[idx] = m0; a1[idx] = m1; }
-                else {
-                    u64 v0 = a0[idx] + m0, v1 = a1[idx] + m1;
-                    a0[idx] = v0 >= twoq ? v0 - twoq : v0;
-                    a1[idx] = v1 >= twoq ? v1 - twoq : v1;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    u64* o0 = p.acc + (size_t)b * p.acc_bs + (size_t)row * N + ((size_t)chunk << CL);
-    u64* o1 = o0 + p.acc_cs;
-#pragma unroll
-    for (int kk = 0; kk < 8; kk++) {
-        const int idx = kk * T + tid;
-        const u64 v0 = a0[idx], v1 = a1[idx];
-        o0[idx] = cred(v0 >= twoq ? v0 - twoq : v0, q);
-        o1[idx] = cred(v1 >= twoq ? v1 - twoq : v1, q);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // K3, register-MAC variant of the 512 x 8 kernel. The last radix-8 round leaves every thread with 8 CONSECUTIVE
 // coefficients in registers (stages 9..11 act inside aligned groups of 8), so the MAC consumes them right there:
@@ -715,7 +613,6 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, u64 tok) {
 }
 __device__ __forceinline__ ulonglong2 ldg128(const u64* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
 
-template <int PREF>
 __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams p) {
     constexpr int CL = 12, T = 512;
     extern __shared__ u64 smem[];
@@ -740,13 +637,6 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
     if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(T) : "memory");
     __syncthreads();
     u64 raw[8];
-    if (PREF) {
-        const int d0 = own_d == 0 ? 1 : 0;
-        if (d0 < p.nd) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d0 * p.p1_ds + k * T + tid];
-        }
-    }
     u64 tok = 0;
     bool pending = false;      // a tile read phase is outstanding: wait for it before overwriting the tile
     for (int d = 0; d < p.nd; d++) {
@@ -759,14 +649,12 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
         if (!own) {
             {
                 double x[8];
-                if (!PREF) {
+                {
 #pragma unroll
                     for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d * p.p1_ds + k * T + tid];
                     // pull the next digit's tile (32 KB = 256 lines) from HBM into L2 while this digit is processed
                     if (KS_L2_PREFETCH && dn < p.nd && tid < 256)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(P1row + (size_t)dn * p.p1_ds + tid * 16));
-                    if (KS_L2_PREFETCH_EVK && d + 1 < p.nd)   // next digit's key rows (both components), 256 lines each
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.evk + (size_t)(d + 1) * p.evk_ds + erow + (tid < 256 ? 0 : p.evk_cs) + (tid & 255) * 16));
                 }
 #pragma unroll
                 for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)raw[k]);
@@ -821,11 +709,6 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
             ulonglong2 k0[2], k1[2];
 #pragma unroll
             for (int j = 0; j < 2; j++) { k0[j] = ldg128(e0 + 4 * h + 2 * j); k1[j] = ldg128(e1 + 4 * h + 2 * j); }
-            if (PREF && h == 1 && !own && dn < p.nd) {
-                // next digit's tile: issued here so that the loads fly during the second MAC half and the barrier wait
-#pragma unroll
-                for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)dn * p.p1_ds + k * T + tid];
-            }
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const int pj = 2 * h + j;
@@ -1009,19 +892,11 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         }
         // algorithmic bytes: P1 read once + accumulators written once + evk once per launch
         ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * fp.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
-        static const int k3v_env = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 10; }();
-        const bool vec_ok = aligned16(cp.evk) && aligned16(cp.cx) && aligned16(cp.acc) && even_words(cp.evk_ds, cp.evk_cs) &&
-                            even_words(cp.cx_rs, cp.cx_bs) && even_words(cp.acc_cs, cp.acc_bs);
-        const int k3v = (k3v_env >= 9 && !vec_ok) ? 8 : k3v_env;
-        if (k3v == 9) {
-            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_fp8r_kernel<1><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
-        } else if (k3v == 10) {
-            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_fp8r_kernel<0><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
-        } else if (k3v == 8) {
-            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_fp8_kernel<<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        // LGPU_K3_VARIANT=0 selects the 256 x 16 shared-memory-MAC kernel (kept as the cross-check of the default one)
+        static const int k3v = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 10; }();
+        if (k3v != 0) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8r_kernel<<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
         } else {
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ks_chunk_mac_kernel<true><<<dim3(batch, chunks, fp.nrows), 256, smem, st>>>(cp);
@@ -1112,7 +987,8 @@ __global__ void __launch_bounds__(256, 2) fz_chunk_epi_kernel(FzChunkParams p) {
     }
 }
 
-// high-occupancy FP64 variant of the same kernel (512 threads x 8 elements, see ks_chunk_mac_fp8_kernel)
+// high-occupancy FP64 variant of the same kernel (512 threads x 8 elements, last round and epilogue in registers,
+// see ks_chunk_mac_fp8r_kernel)
 __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams p) {
     constexpr int CL = 12, T = 512;
     extern __shared__ u64 smem[];

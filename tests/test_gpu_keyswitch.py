@@ -1,5 +1,7 @@
 """GPU parity (bit-exact vs the oracle) of basis extension, rescaling, automorphisms, the rlwe.Evaluator
 key-switch family and the CKKS MulRelin+Rescale sequence. Run with -m gpu on the B200 box."""
+import os
+
 import numpy as np
 import pytest
 
@@ -7,6 +9,7 @@ from oracle import oracle as O
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
 U64 = np.uint64
 
 
@@ -481,3 +484,18 @@ def test_unaligned_buffers():
     with pytest.raises(lb.LgpuError, match="16-byte aligned"):
         lb.CKKSEvaluator(ctx, rlk).MulRelinRescaleNew(odd(a), ctx.to_device(a))
     ctx.close()
+
+
+@pytest.mark.parametrize("env", ["LGPU_K3_VARIANT=0", "LGPU_K2_J4=0", "LGPU_FZ_VARIANT=0", "LGPU_NO_FUSED_KS=1", "LGPU_NO_FP64_NTT=1",
+                                 "LGPU_NO_SIDE_STREAM=1", "LGPU_BATCH_CHUNK=1"])
+def test_fallback_kernel_variants_stay_bit_exact(env):
+    """The development switches select the older / unfused kernels (read once per process, hence a subprocess); every
+    one of them must reproduce the oracle on the fused-pipeline cases too."""
+    import subprocess
+    import sys
+    k, v = env.split("=")
+    e = dict(os.environ, **{k: v})
+    root = os.path.dirname(HERE)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_keyswitch.py"), "-m", "gpu", "-x", "-q", "-k",
+                        "fused_pipeline_logn13 or mulrelin_rescale_small"], cwd=root, env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
