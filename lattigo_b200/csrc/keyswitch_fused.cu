@@ -158,6 +158,12 @@ enum { PRO_MODUP = 0, PRO_BCAST = 1 };
 #ifndef KS_STRIDED_J4_MINB
 #define KS_STRIDED_J4_MINB 4
 #endif
+#ifndef KS_FULL
+#define KS_FULL 1
+#endif
+#ifndef KS_STREAM
+#define KS_STREAM 0   // (measured: no gain) P1 tiles and key rows are read once per CTA: streaming loads keep the twiddles in L1
+#endif
 #ifndef KS_L2_PREFETCH
 #define KS_L2_PREFETCH 1
 #endif
@@ -350,12 +356,22 @@ __global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(
     const int l = l0 + lx;
     u64* out = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N + l;
     u64 e[R];
+    if (KS_FULL && nS == NSMAX) {          // full digit (every digit but possibly the last): no per-source predication
 #pragma unroll
-    for (int k = 0; k < R; k++) {
-        u64 y[NSMAX];
+        for (int k = 0; k < R; k++) {
+            u64 y[NSMAX];
 #pragma unroll
-        for (int i = 0; i < NSMAX; i++) y[i] = i < nS ? s_y[(i * R + k) * LB + lx] : 0;
-        e[k] = ks_ext<NSMAX>(y, nS, (int)s_v[k * LB + lx], s_c[jj], s_vt[jj], half_t, q, qinv);
+            for (int i = 0; i < NSMAX; i++) y[i] = s_y[(i * R + k) * LB + lx];
+            e[k] = ks_ext<NSMAX>(y, NSMAX, (int)s_v[k * LB + lx], s_c[jj], s_vt[jj], half_t, q, qinv);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            u64 y[NSMAX];
+#pragma unroll
+            for (int i = 0; i < NSMAX; i++) y[i] = i < nS ? s_y[(i * R + k) * LB + lx] : 0;
+            e[k] = ks_ext<NSMAX>(y, nS, (int)s_v[k * LB + lx], s_c[jj], s_vt[jj], half_t, q, qinv);
+        }
     }
     if constexpr (FP) {
         const double fq = L.fq, fqinv = L.fqinv;
@@ -611,7 +627,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, u64 tok) {
                      : "=r"(done) : "r"(bar), "l"(tok) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ ulonglong2 ldg128(const u64* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
+__device__ __forceinline__ ulonglong2 ldg128(const u64* p) {
+    return KS_STREAM ? __ldcs(reinterpret_cast<const ulonglong2*>(p)) : __ldg(reinterpret_cast<const ulonglong2*>(p));
+}
 
 __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams p) {
     constexpr int CL = 12, T = 512;
@@ -626,7 +644,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
     const LimbConst L = p.limbs[limb];
     const int s1 = p.logN - CL;
     const int N = 1 << p.logN;
-    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
+    const u64 q = L.q, qinv = L.qinv;
     const double fq = L.fq, fqinv = L.fqinv;
     const double* tw = L.ftw_fwd;
     const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
@@ -651,7 +669,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                 double x[8];
                 {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) raw[k] = P1row[(size_t)d * p.p1_ds + k * T + tid];
+                    for (int k = 0; k < 8; k++) raw[k] = KS_STREAM ? __ldcs(P1row + (size_t)d * p.p1_ds + k * T + tid) : P1row[(size_t)d * p.p1_ds + k * T + tid];
                     // pull the next digit's tile (32 KB = 256 lines) from HBM into L2 while this digit is processed
                     if (KS_L2_PREFETCH && dn < p.nd && tid < 256)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(P1row + (size_t)dn * p.p1_ds + tid * 16));
@@ -719,12 +737,10 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                 ulonglong2* A0 = accs + (size_t)(0 * 4 + pj) * T + tid;
                 ulonglong2* A1 = accs + (size_t)(1 * 4 + pj) * T + tid;
                 if (d != 0) {
+                    // plain adds: every term is < 2q < 2^47 and there are at most kMaxDigits of them, so the u64 sums cannot
+                    // overflow; one Barrett step in the epilogue gives the canonical residue the reference's Reduce leaves
                     const ulonglong2 c0 = *A0, c1 = *A1;
-                    u64 v;
-                    v = c0.x + m0.x; m0.x = v >= twoq ? v - twoq : v;
-                    v = c0.y + m0.y; m0.y = v >= twoq ? v - twoq : v;
-                    v = c1.x + m1.x; m1.x = v >= twoq ? v - twoq : v;
-                    v = c1.y + m1.y; m1.y = v >= twoq ? v - twoq : v;
+                    m0.x += c0.x; m0.y += c0.y; m1.x += c1.x; m1.y += c1.y;
                 }
                 *A0 = m0; *A1 = m1;
             }
@@ -736,8 +752,8 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
     for (int pj = 0; pj < 4; pj++) {
         const ulonglong2 c0 = accs[(size_t)(0 * 4 + pj) * T + tid], c1 = accs[(size_t)(1 * 4 + pj) * T + tid];
         ulonglong2 r0, r1;
-        r0.x = cred(c0.x >= twoq ? c0.x - twoq : c0.x, q); r0.y = cred(c0.y >= twoq ? c0.y - twoq : c0.y, q);
-        r1.x = cred(c1.x >= twoq ? c1.x - twoq : c1.x, q); r1.y = cred(c1.y >= twoq ? c1.y - twoq : c1.y, q);
+        r0.x = bred_add(c0.x, q, L.bred_hi); r0.y = bred_add(c0.y, q, L.bred_hi);
+        r1.x = bred_add(c1.x, q, L.bred_hi); r1.y = bred_add(c1.y, q, L.bred_hi);
         *reinterpret_cast<ulonglong2*>(o0 + 2 * pj) = r0;
         *reinterpret_cast<ulonglong2*>(o1 + 2 * pj) = r1;
     }
