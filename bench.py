@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="ciphertext pairs per GPU per step")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="(reference arm) pairs per step; 0 = one per core")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=8, help="ciphertext pairs per pipeline chunk of the host entry point (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -331,12 +332,12 @@ def gpu_main(args):
         ha.copy_(a); hb.copy_(b)
         torch.cuda.synchronize()
         na, nb_, no = ha.numpy().view(np.uint64), hb.numpy().view(np.uint64), ho.numpy().view(np.uint64)
-        ev.MulRelinRescaleHost(na, nb_, no, chunk=8)     # warm-up (allocators, page touching)
+        ev.MulRelinRescaleHost(na, nb_, no, chunk=args.e2e_chunk)     # warm-up (allocators, page touching)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
         for _ in range(e2e_steps):
-            ev.MulRelinRescaleHost(na, nb_, no, chunk=8)
+            ev.MulRelinRescaleHost(na, nb_, no, chunk=args.e2e_chunk)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         td = torch.tensor([dt], device=dev, dtype=torch.float64)
