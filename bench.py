@@ -257,7 +257,7 @@ def gpu_main(args):
     if rank == 0:
         import ctypes
         L = _lib.lib()
-        nk = 8
+        nk = 9
         ms = (ctypes.c_double * nk)(); by = (ctypes.c_double * nk)()
         sc = (ctypes.c_ulonglong * nk)(); kn = (ctypes.c_ulonglong * nk)()
         L.lgpu_profile_enable(1)
@@ -266,7 +266,7 @@ def gpu_main(args):
         torch.cuda.synchronize()
         L.lgpu_profile_enable(0)
         L.lgpu_profile_read(ms, by, sc, kn)
-        names = ["ntt_fwd", "ntt_inv", "vecop", "modup", "mac", "tensor", "automorphism", "fused"]
+        names = ["ntt_fwd", "ntt_inv", "vecop", "modup", "mac", "tensor", "automorphism", "fused", "epilogue"]
         classes = {names[i]: {"ms": ms[i], "alg_GB": by[i] / 1e9, "scopes": int(sc[i]), "kernels": int(kn[i]),
                               "alg_GBs": (by[i] / 1e9) / (ms[i] * 1e-3) if ms[i] > 0 else None} for i in range(nk) if sc[i]}
         peaks = {}
@@ -281,17 +281,20 @@ def gpu_main(args):
         dom = max(range(nk), key=lambda i: ms[i])
         kernel_names = {
             "mac": "ks_chunk_mac_fp8r_kernel (K3: chunk-pass NTT, 12 stages on the FP64 pipe, + key-switch MAC over all digits from registers)",
-            "fused": "ks_strided_kernel / fz_chunk_epi_kernel (basis extension folded into the strided NTT pass; ModDown / rescale epilogues)",
+            "fused": "ks_strided_j4_kernel (K2: basis extension folded into the strided NTT pass, y/v tile shared by 8 target rows)",
+            "epilogue": "fz_chunk_epi_fp8_kernel (chunk-pass NTT + ModDown / Rescale epilogue from registers)",
             "ntt_fwd": "ntt strided + chunk pass kernels (forward)", "ntt_inv": "ntt chunk + strided pass kernels (inverse)",
             "modup": "ks_prepare_kernel / modup_kernel", "vecop": "vecop_kernel", "tensor": "ckks_tensor_kernel",
             "automorphism": "auto_ntt_kernel"}
         ach = (by[dom] / 1e9) / (ms[dom] * 1e-3) if ms[dom] > 0 else 0.0
         traffic = None
         try:
+            # ncu dram bytes of the class's launches per ciphertext pair (one --set full capture, see the file), scaled to
+            # the average launch scope of this run: per_ct x pairs per step / scopes per step
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
             ent = tr.get(names[dom])
             if ent and ent.get("preset") == args.preset:
-                traffic = ent["dram_bytes_per_launch"]
+                traffic = ent["dram_bytes_per_ct"] * B * args.steps / max(1, int(sc[dom]))
         except Exception:
             pass
         # standalone transform rate (BASELINE metric "NTT GB/s vs roofline"): Ring.NTT on all Q limbs of the preset,
@@ -318,8 +321,7 @@ def gpu_main(args):
                 "traffic": traffic, "avg_launch_ms": ms[dom] / max(1, int(sc[dom])), "alg_bytes_per_launch": by[dom] / max(1, int(sc[dom])),
                 "share_of_step": ms[dom] / tot, "ntt_standalone": ntt_standalone, "classes": classes,
                 "note": "classes: summed CUDA-event time of launch scopes over the same K steps re-run with the event profiler on; "
-                        "in that re-run the integer-row chains stay on the main stream (normally a side stream), so class times do "
-                        "not overlap and add up to the step"}
+                        "all chains run on the caller's stream, so class times do not overlap and add up to the step"}
     barrier()
 
     # ---- e2e through the host-buffer C-ABI entry point (pinned host memory, copies inside the timed region) ------

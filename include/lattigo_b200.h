@@ -271,7 +271,8 @@ enum lgpu_kclass {
     LGPU_KCLASS_MAC,           /* key-switch multiply-accumulate */
     LGPU_KCLASS_TENSOR,
     LGPU_KCLASS_AUTOMORPHISM,
-    LGPU_KCLASS_FUSED,
+    LGPU_KCLASS_FUSED,         /* K2: basis extension / rescale prologue folded into the strided transform pass */
+    LGPU_KCLASS_EPILOGUE,      /* chunk transform pass with the ModDown / Rescale epilogue */
     LGPU_KCLASS_COUNT
 };
 /* total number of CUDA kernels this library has launched in the process */

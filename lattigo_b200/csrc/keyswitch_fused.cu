@@ -38,8 +38,11 @@ struct SideStream {
 };
 static SideStream* side_stream(int device) {
     static thread_local SideStream ss[16];
-    static const int off = [] { const char* e = getenv("LGPU_NO_SIDE_STREAM"); return e && atoi(e) ? 1 : 0; }();
-    if (off || device < 0 || device >= 16) return nullptr;
+    // Opt-in (LGPU_SIDE_STREAM=1): running the integer-row chain next to the FP64-row chain gains ~1 % when one stream
+    // drives the GPU, but the shared side stream couples otherwise independent caller streams (the host-buffer
+    // pipeline lost a third of its throughput to it), so the default keeps every chain on the caller's stream.
+    static const int on = [] { const char* e = getenv("LGPU_SIDE_STREAM"); return e && atoi(e) ? 1 : 0; }();
+    if (!on || device < 0 || device >= 16) return nullptr;
     SideStream& x = ss[device];
     if (!x.s) {
         if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
@@ -1180,13 +1183,15 @@ int moddown_ntt_fused(const Ctx* c, int levelQ, int levelP, const u64* acc, size
     auto scal = [&](const RowMap& rm) { for (int r = 0; r < rm.nrows; r++) { const int i = rm.drow[r]; cp.s[r] = c->Q[i] - c->mdc_PtoQ[(size_t)levelP * c->nQ + i]; } };
     cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
     if (in.nrows) {
-        ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows * (D ? 5.0 : 4.0), 2);
-        sp.rm = in; if (ks_launch_strided<false>(s1, np, sp, dim3(gx, in.nrows, Z), sint)) return -1;
+        { ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows, 1);
+          sp.rm = in; if (ks_launch_strided<false>(s1, np, sp, dim3(gx, in.nrows, Z), sint)) return -1; }
+        ProfScope ps(LGPU_KCLASS_EPILOGUE, sint, 8.0 * N * Z * in.nrows * ((D ? 5.0 : 4.0) - 1.0), 1);
         cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), sint)) return -1;
     }
     if (fp.nrows) {
-        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows * (D ? 5.0 : 4.0), 2);
-        sp.rm = fp; if (ks_launch_strided<true>(s1, np, sp, dim3(gx, fp.nrows, Z), st)) return -1;
+        { ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows, 1);
+          sp.rm = fp; if (ks_launch_strided<true>(s1, np, sp, dim3(gx, fp.nrows, Z), st)) return -1; }
+        ProfScope ps(LGPU_KCLASS_EPILOGUE, st, 8.0 * N * Z * fp.nrows * ((D ? 5.0 : 4.0) - 1.0), 1);
         cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1;
     }
     join_side(c, st, sint);
@@ -1231,13 +1236,15 @@ int div_round_last_ntt_fused(const Ctx* c, int level, const u64* X, size_t x_cs,
     auto scal = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) cp.s[k] = c->rescaleQ[(size_t)(level - 1) * c->nQ + rm.drow[k]]; };
     cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
     if (in.nrows) {
-        ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows * 4.0, 2);
-        sp.rm = in; s0(in); if (ks_launch_strided<false, PRO_BCAST>(s1, 1, sp, dim3(gx, in.nrows, Z), sint)) return -1;
+        { ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows, 1);
+          sp.rm = in; s0(in); if (ks_launch_strided<false, PRO_BCAST>(s1, 1, sp, dim3(gx, in.nrows, Z), sint)) return -1; }
+        ProfScope ps(LGPU_KCLASS_EPILOGUE, sint, 8.0 * N * Z * in.nrows * (4.0 - 1.0), 1);
         cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), sint)) return -1;
     }
     if (fp.nrows) {
-        ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows * 4.0, 2);
-        sp.rm = fp; s0(fp); if (ks_launch_strided<true, PRO_BCAST>(s1, 1, sp, dim3(gx, fp.nrows, Z), st)) return -1;
+        { ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows, 1);
+          sp.rm = fp; s0(fp); if (ks_launch_strided<true, PRO_BCAST>(s1, 1, sp, dim3(gx, fp.nrows, Z), st)) return -1; }
+        ProfScope ps(LGPU_KCLASS_EPILOGUE, st, 8.0 * N * Z * fp.nrows * (4.0 - 1.0), 1);
         cp.rm = fp; scal(fp); if (fz_launch_chunk<true>(cp, dim3(chunks, fp.nrows, Z), st)) return -1;
     }
     join_side(c, st, sint);

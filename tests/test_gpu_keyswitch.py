@@ -487,7 +487,7 @@ def test_unaligned_buffers():
 
 
 @pytest.mark.parametrize("env", ["LGPU_K3_VARIANT=0", "LGPU_K2_J4=0", "LGPU_FZ_VARIANT=0", "LGPU_NO_FUSED_KS=1", "LGPU_NO_FP64_NTT=1",
-                                 "LGPU_NO_SIDE_STREAM=1", "LGPU_BATCH_CHUNK=1"])
+                                 "LGPU_SIDE_STREAM=1", "LGPU_BATCH_CHUNK=1"])
 def test_fallback_kernel_variants_stay_bit_exact(env):
     """The development switches select the older / unfused kernels (read once per process, hence a subprocess); every
     one of them must reproduce the oracle on the fused-pipeline cases too."""
