@@ -1,6 +1,7 @@
 // capi2.cu -- extern "C" entry points for automorphisms, basis extension, rescaling, the rlwe.Evaluator
 // key-switch family and the fused CKKS batch ops (include/lattigo_b200.h).
 #include <algorithm>
+#include <mutex>
 #include <cstring>
 #include "../../include/lattigo_b200.h"
 #include "composite.h"
@@ -258,20 +259,26 @@ int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64
     const size_t N = c.N, nq = level + 1, nqo = nq - nb_rescales;
     const size_t in_words = 2 * nq * N, out_words = 2 * nqo * N;
     LGPU_CUDA_OK(cudaSetDevice(c.device));
-    cudaStream_t st[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr};
-    u64 *dA[2] = {nullptr, nullptr}, *dB[2] = {nullptr, nullptr}, *dO[2] = {nullptr, nullptr};
+    // Two independent streams, each doing H2D -> compute -> D2H for alternating chunks: the copies of one chunk overlap
+    // the compute of the other (copy engines run concurrently with the SMs). Streams and staging buffers live in the
+    // context; one host-pipeline call at a time per context.
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Ctx::HostPipe& hp = ctx->c.host_pipe;
     int rc = 0;
+    const size_t need[3] = {chunk * in_words, chunk * in_words, chunk * out_words};
     for (int i = 0; i < 2 && !rc; i++) {
-        if (cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaMalloc(&dA[i], chunk * in_words * 8) != cudaSuccess || cudaMalloc(&dB[i], chunk * in_words * 8) != cudaSuccess ||
-            cudaMalloc(&dO[i], chunk * out_words * 8) != cudaSuccess) {
-            lgpu::set_error("allocation failed in mulrelin_rescale_batch_host");
-            rc = -1;
+        if (!hp.st[i] && cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking) != cudaSuccess) rc = -1;
+        for (int k = 0; k < 3 && !rc; k++) {
+            if (hp.buf[i][k] && hp.cap[k] >= need[k]) continue;
+            if (hp.buf[i][k]) { cudaStreamSynchronize(hp.st[i]); cudaFree(hp.buf[i][k]); hp.buf[i][k] = nullptr; }
+            if (cudaMalloc(&hp.buf[i][k], need[k] * 8) != cudaSuccess) rc = -1;
         }
     }
-    // Two independent streams, each doing H2D -> compute -> D2H for alternating chunks: the copies of one
-    // chunk overlap the compute of the other (copy engines run concurrently with the SMs).
+    if (rc) lgpu::set_error("allocation failed in mulrelin_rescale_batch_host");
+    else for (int k = 0; k < 3; k++) hp.cap[k] = std::max(hp.cap[k], need[k]);
+    cudaStream_t* st = hp.st;
+    u64 *dA[2] = {hp.buf[0][0], hp.buf[1][0]}, *dB[2] = {hp.buf[0][1], hp.buf[1][1]}, *dO[2] = {hp.buf[0][2], hp.buf[1][2]};
     for (int k = 0, i = 0; !rc && k < batch; k += chunk, i ^= 1) {
         const int nb = std::min(chunk, batch - k);
         if (cudaMemcpyAsync(dA[i], ct_a_host + (size_t)k * in_words, nb * in_words * 8, cudaMemcpyHostToDevice, st[i]) != cudaSuccess ||
@@ -286,11 +293,6 @@ int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64
     }
     for (int i = 0; i < 2; i++) {
         if (st[i]) cudaStreamSynchronize(st[i]);
-    }
-    for (int i = 0; i < 2; i++) {
-        cudaFree(dA[i]); cudaFree(dB[i]); cudaFree(dO[i]);
-        if (done[i]) cudaEventDestroy(done[i]);
-        if (st[i]) cudaStreamDestroy(st[i]);
     }
     if (!rc) {
         cudaError_t e = cudaGetLastError();

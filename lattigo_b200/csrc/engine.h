@@ -99,6 +99,13 @@ struct Ctx {
     size_t scratch_words = 0;
     // automorphism index cache: galEl -> device index table (u32[N])
     std::vector<std::pair<u64, unsigned int*>> auto_index;
+    // staging state of the *_host entry points, created on first use and kept for the life of the context (allocating
+    // and freeing ~2 GB of device staging per call was a visible, noisy part of the end-to-end time)
+    struct HostPipe {
+        cudaStream_t st[2] = {nullptr, nullptr};
+        u64* buf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [stream][A, B, out]
+        size_t cap[3] = {0, 0, 0};                                                       // words per buffer kind
+    } host_pipe;
 };
 
 // 128-bit vector accesses need 16-byte aligned bases and even strides (in words); callers that hand in odd row offsets
