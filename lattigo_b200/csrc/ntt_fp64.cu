@@ -17,6 +17,10 @@
 #include "modarith.cuh"
 #include "ntt_arith.cuh"
 
+#ifndef NTT_FP_REG_OUT
+#define NTT_FP_REG_OUT 0
+#endif
+
 namespace lgpu {
 
 struct FpParams {
@@ -201,8 +205,21 @@ __global__ void __launch_bounds__((1 << CL) / 16, 2) ntt_fp_chunk_fwd_kernel(FpP
         double t3[15];
         fp_load_tw<CL, R0 + R1, R2>(t3, tw, s1, chunk, tid);
         __syncthreads();
+#if NTT_FP_REG_OUT
         fp_fwd_round_tw_out<CL, R0 + R1, R2>(fsm, t3, q, qinv, tid, dst);   // 16 consecutive coefficients per thread
         __syncthreads();                                                   // tile reads done before the next element's stores
+#else
+        // copy-out through the tile: every store instruction covers 32 consecutive words (measured 7 % faster than
+        // writing the last round's 16 consecutive coefficients per thread straight from registers)
+        fp_fwd_round_tw<CL, R0 + R1, R2>(fsm, t3, q, qinv, tid);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int idx = k * T + tid;
+            dst[idx] = fp_canon(fsm[fpad(idx)], q, qinv);
+        }
+        __syncthreads();
+#endif
     }
 }
 
