@@ -1,26 +1,14 @@
 // capi.cu -- extern "C" entry points declared in include/lattigo_b200.h (context, memory, NTT, vec ops).
 #include <cstring>
-#include "../../include/lattigo_b200.h"
-#include "engine.h"
+#include "capi_common.h"
 
 using namespace lgpu;
 
-struct lgpu_ctx {
-    Ctx c;
-};
 
 // NULL means the CUDA default stream (same convention as the runtime API), so that callers which pass their
 // framework's current stream (0 for torch's default stream) stay ordered with their own work.
 static inline cudaStream_t pick_stream(lgpu_ctx* ctx, void* stream) { (void)ctx; return (cudaStream_t)stream; }
 
-#define REQUIRE(cond, msg)                 \
-    do {                                   \
-        if (!(cond)) {                     \
-            lgpu::set_error(msg);          \
-            return -1;                     \
-        }                                  \
-    } while (0)
-#define REQUIRE_DEVICE(ctx) REQUIRE((ctx) && (ctx)->c.device >= 0, "this context was created host-only (device < 0): no device execution")
 
 namespace lgpu {
 // rows 0..level of ring Q or P -> global limb indices

@@ -3,26 +3,12 @@
 #include <algorithm>
 #include <mutex>
 #include <cstring>
-#include "../../include/lattigo_b200.h"
+#include "capi_common.h"
 #include "composite.h"
 
 using namespace lgpu;
 
-struct lgpu_ctx {
-    Ctx c;
-};
 
-#define REQUIRE(cond, msg)                 \
-    do {                                   \
-        if (!(cond)) {                     \
-            lgpu::set_error(msg);          \
-            return -1;                     \
-        }                                  \
-    } while (0)
-// the key-switch family moves 128 bits per access: polynomial blocks must be 16-byte aligned with even strides
-#define AL(p) ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)
-#define REQUIRE_ALIGNED(cond) REQUIRE(cond, "polynomial buffers and evaluation keys must be 16-byte aligned with even strides (words)")
-#define REQUIRE_DEVICE(ctx) REQUIRE((ctx) && (ctx)->c.device >= 0, "this context was created host-only (device < 0): no device execution")
 
 static inline cudaStream_t S(void* stream) { return (cudaStream_t)stream; }
 

@@ -1,0 +1,28 @@
+// capi_common.h -- shared by the extern "C" translation units (capi.cu, capi2.cu, ringmisc.cu): the opaque handle,
+// argument-check macros and the row-map helpers.
+#pragma once
+#include <cstdint>
+#include "../../include/lattigo_b200.h"
+#include "engine.h"
+
+struct lgpu_ctx {
+    lgpu::Ctx c;
+};
+
+#define REQUIRE(cond, msg)                 \
+    do {                                   \
+        if (!(cond)) {                     \
+            lgpu::set_error(msg);          \
+            return -1;                     \
+        }                                  \
+    } while (0)
+#define REQUIRE_DEVICE(ctx) REQUIRE((ctx) && (ctx)->c.device >= 0, "this context was created host-only (device < 0): no device execution")
+// the key-switch family moves 128 bits per access: polynomial blocks must be 16-byte aligned with even strides
+#define AL(p) ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)
+#define REQUIRE_ALIGNED(cond) REQUIRE(cond, "polynomial buffers and evaluation keys must be 16-byte aligned with even strides (words)")
+
+namespace lgpu {
+// rows 0..level of ring Q or P -> global limb indices (capi.cu)
+int make_rowmap(const Ctx& c, int ring, int level, RowMap& rm);
+int make_rowmap_single(const Ctx& c, int ring, int limb, RowMap& rm);
+}  // namespace lgpu

@@ -2,18 +2,13 @@
 // Shift, MultByMonomial, MapSmallDimensionToLargerDimensionNTT, ExtendBasisSmallNormAndCenter.
 // Pure data movement (+ a negation): one thread per output coefficient, coalesced writes.
 #include <cstring>
-#include "../../include/lattigo_b200.h"
-#include "engine.h"
+#include "capi_common.h"
 #include "modarith.cuh"
 
 using namespace lgpu;
 
-struct lgpu_ctx {
-    Ctx c;
-};
 
 namespace lgpu {
-int make_rowmap(const Ctx& c, int ring, int level, RowMap& rm);
 
 struct MoveParams {
     const LimbConst* limbs;
@@ -87,14 +82,6 @@ __global__ void __launch_bounds__(256) extend_small_norm_kernel(const u64* inq0,
 }
 }  // namespace lgpu
 
-#define REQUIRE(cond, msg)                 \
-    do {                                   \
-        if (!(cond)) {                     \
-            lgpu::set_error(msg);          \
-            return -1;                     \
-        }                                  \
-    } while (0)
-#define REQUIRE_DEVICE(ctx) REQUIRE((ctx) && (ctx)->c.device >= 0, "this context was created host-only (device < 0): no device execution")
 
 // in-place calls go through a stream-ordered temporary copy of the input (the reference allows p1 == p2 for both)
 static int move_common(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t* out, int k, int batch, size_t batch_stride, bool monomial,
