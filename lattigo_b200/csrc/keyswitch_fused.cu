@@ -617,6 +617,16 @@ __device__ __forceinline__ void fp8_round(double* sm, const double (&t)[7], doub
 //     mbarrier: arrive right after the last-round reads, wait just before the next digit's first-round stores.
 // Warps therefore drift apart inside a CTA and the integer MAC of one warp overlaps the FP64 butterflies of another.
 // ------------------------------------------------------------------------------------------------------------
+// The integer consumers of a transformed coefficient (MRedLazy with a key word, the ModDown / Rescale MRed) accept ANY
+// representative below 2^64, so the canonicalisation (3 FP64 + compare + add + conversion) is replaced by one biased
+// conversion: |x| < (10 + logN) q < 2^51 (the fp_ok bound), hence x + (10 + logN) q lies in [0, 2^52) and
+// bits(x + (10 + logN) q + 2^52) & (2^52 - 1) is that value as an integer.
+#ifndef KS_LAZY_X
+#define KS_LAZY_X 1
+#endif
+__device__ __forceinline__ u64 fp_biased_u64(double x, double off52) {
+    return (u64)__double_as_longlong(__dadd_rn(x, off52)) & 0x000FFFFFFFFFFFFFull;
+}
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ u64 mbar_arrive(unsigned bar) {
     u64 tok;
@@ -649,6 +659,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
     const int N = 1 << p.logN;
     const u64 q = L.q, qinv = L.qinv;
     const double fq = L.fq, fqinv = L.fqinv;
+    const double off52 = __dmul_rn((double)(10 + p.logN), fq) + 4503599627370496.0;   // (10 + logN) q + 2^52, exact
     const double* tw = L.ftw_fwd;
     const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
     const u64* P1row = p.P1 + (size_t)b * p.p1_bs + (size_t)row * N + ((size_t)chunk << CL);
@@ -719,7 +730,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 8; k++) xv[k] = fp_canon(x[k], fq, fqinv);
+                for (int k = 0; k < 8; k++) xv[k] = KS_LAZY_X ? fp_biased_u64(x[k], off52) : fp_canon(x[k], fq, fqinv);
             }
         } else {
 #pragma unroll
@@ -1020,6 +1031,7 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
     const int N = 1 << p.logN;
     const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
     const double fq = L.fq, fqinv = L.fqinv;
+    const double off52 = __dmul_rn((double)(10 + p.logN), fq) + 4503599627370496.0;   // (10 + logN) q + 2^52, exact
     const double* tw = L.ftw_fwd;
     const u64 sc = p.s[blockIdx.y];
     const int zc = z / p.nb, zb = z % p.nb;
@@ -1080,8 +1092,10 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         ulonglong2 r;
-        r.x = mred(fp_canon(x[2 * j], fq, fqinv) + twoq - a[j].x, sc, q, qinv);
-        r.y = mred(fp_canon(x[2 * j + 1], fq, fqinv) + twoq - a[j].y, sc, q, qinv);
+        const u64 xa = KS_LAZY_X ? fp_biased_u64(x[2 * j], off52) : fp_canon(x[2 * j], fq, fqinv);
+        const u64 xb = KS_LAZY_X ? fp_biased_u64(x[2 * j + 1], off52) : fp_canon(x[2 * j + 1], fq, fqinv);
+        r.x = mred(xa + twoq - a[j].x, sc, q, qinv);
+        r.y = mred(xb + twoq - a[j].y, sc, q, qinv);
         if (D) { r.x = cred(r.x + d[j].x, q); r.y = cred(r.y + d[j].y, q); }
         *reinterpret_cast<ulonglong2*>(out + 8 * tid + 2 * j) = r;
     }
