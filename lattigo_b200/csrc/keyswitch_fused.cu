@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
 bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
     static const int off = [] { const char* e = getenv("LGPU_NO_FUSED_KS"); return e && atoi(e) ? 1 : 0; }();
     if (off || c->ring_type != 0) return false;
-    if (c->logN < 13 || c->logN > 17) return false;            // two-pass transforms with a 4096-element chunk pass
+    if (c->logN < 13 || c->logN > 16) return false;            // two-pass transforms with a 4096-element chunk pass; validated sizes only (2^17 takes the unfused kernels)
     if (evk.levelP < 1 || evk.pw2 != 0) return false;          // multiple-P path only
     const int k = evk.levelP + 1;
     const int nd = base_rns_decomposition_vector_size(levelQ, evk.levelP);
@@ -1128,7 +1128,7 @@ static void split_rows(const Ctx* c, int limb0, int nrows, RowMap& fp, RowMap& i
 
 bool fz_applicable(const Ctx* c, int levelQ, int levelP) {
     static const int off = [] { const char* e = getenv("LGPU_NO_FUSED_KS"); return e && atoi(e) ? 1 : 0; }();
-    if (off || c->ring_type != 0 || c->logN < 13 || c->logN > 17) return false;
+    if (off || c->ring_type != 0 || c->logN < 13 || c->logN > 16) return false;
     if (levelQ + 1 > kMaxRows || levelP + 1 > 8) return false;
     for (int i = 0; i <= levelQ; i++) if (!c->h_limbs[i].fp_ok && c->h_limbs[i].fwd_mask != 0) return false;
     return true;
