@@ -48,3 +48,27 @@ def test_host_only_context_refuses_device_work_and_bad_params():
     with pytest.raises(lb.LgpuError):
         lb.Context(8, [97], device=-1)                 # 97 != 1 mod 512
     ctx.close()
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/lattigo_b200.h must compile as C99 (what cgo feeds to the C compiler) and as C++,
+    with plain pointers / sizes only (no torch or CUDA types in any signature)."""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    src = open(os.path.join(inc, "lattigo_b200.h")).read()
+    for banned in ("torch", "at::", "cudaStream_t", "std::", "#include <cuda"):
+        assert banned not in src, banned
+    gcc = shutil.which("gcc") or "/opt/gcc/bin/gcc"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "h.c")
+        open(c, "w").write('#include "lattigo_b200.h"\nint main(void) { return (int)LGPU_OP_COUNT - (int)LGPU_OP_COUNT; }\n')
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, c], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        gpp = shutil.which("g++")
+        if gpp:
+            r = subprocess.run([gpp, "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, c], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
