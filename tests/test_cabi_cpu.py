@@ -59,7 +59,8 @@ def test_header_is_plain_c():
     import tempfile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     inc = os.path.join(root, "include")
-    src = open(os.path.join(inc, "lattigo_b200.h")).read()
+    import re
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, "lattigo_b200.h")).read(), flags=re.S)    # declarations only
     for banned in ("torch", "at::", "cudaStream_t", "std::", "#include <cuda"):
         assert banned not in src, banned
     gcc = shutil.which("gcc") or "/opt/gcc/bin/gcc"
