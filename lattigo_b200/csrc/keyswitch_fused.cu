@@ -783,7 +783,7 @@ bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
     if (evk.levelP < 1 || evk.pw2 != 0) return false;          // multiple-P path only
     const int k = evk.levelP + 1;
     const int nd = base_rns_decomposition_vector_size(levelQ, evk.levelP);
-    if (levelQ + 1 > 64 || nd > kMaxDigits || k > 8) return false;
+    if (levelQ + 1 > 64 || nd > kMaxDigits || k > 4) return false;   // digit sizes validated on the device: 2..4 (larger k takes the unfused kernels)
     for (int i = 0; i <= levelQ; i++) if (!c->h_limbs[i].fp_ok && c->h_limbs[i].fwd_mask != 0) return false;
     for (int j = 0; j <= evk.levelP; j++) if (!c->h_limbs[c->nQ + j].fp_ok && c->h_limbs[c->nQ + j].fwd_mask != 0) return false;
     return true;
@@ -1129,7 +1129,7 @@ static void split_rows(const Ctx* c, int limb0, int nrows, RowMap& fp, RowMap& i
 bool fz_applicable(const Ctx* c, int levelQ, int levelP) {
     static const int off = [] { const char* e = getenv("LGPU_NO_FUSED_KS"); return e && atoi(e) ? 1 : 0; }();
     if (off || c->ring_type != 0 || c->logN < 13 || c->logN > 16) return false;
-    if (levelQ + 1 > kMaxRows || levelP + 1 > 8) return false;
+    if (levelQ + 1 > kMaxRows || levelP + 1 > 4) return false;   // validated source counts only
     for (int i = 0; i <= levelQ; i++) if (!c->h_limbs[i].fp_ok && c->h_limbs[i].fwd_mask != 0) return false;
     return true;
 }
