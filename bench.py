@@ -116,11 +116,17 @@ def reference_main(args):
                    MALLOC_TOP_PAD_="268435456", MALLOC_ARENA_MAX="1")
         os.execve(sys.executable, [sys.executable] + sys.argv, env)
     r = run_cpu_arm(args, args.steps, args.warmup, args.cpu_sample_pairs)
+    from lattigo_b200 import params as presets      # pure-Python parameter literals (does not load the CUDA library)
+    P = presets.PRESETS[args.preset]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "ckks_mulrelin_rescale", "preset": args.preset, "pairs_per_step": r["pairs_per_step"],
+        # same workload description as the product arm (preset, ring degree, limb counts); each step is a bounded sample
+        # of it: one ciphertext pair per host core instead of the 64 pairs per GPU
+        "config": {"workload": "ckks_mulrelin_rescale", "preset": args.preset, "logN": P["logN"], "q_limbs": len(P["Q"]), "p_limbs": len(P["P"]),
+                   "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "pairs_per_step": r["pairs_per_step"],
+                   "sample": "one ciphertext pair per host core per step (bounded sample of the batch)",
                    "note": "oracle = C/Python restatement of the reference's pure-Go path (Go toolchain absent); one pair per worker process"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                          "sample": "%d steps x %d ciphertext pairs, one per core" % (args.steps, r["pairs_per_step"])},
