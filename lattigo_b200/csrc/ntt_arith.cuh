@@ -40,6 +40,14 @@ __device__ __forceinline__ void fast_inv_bfly(u64& X, u64& Y, ulonglong2 w, u64 
 #define FP_TWO52 4503599627370496.0   /* 2^52 */
 
 __device__ __forceinline__ double u2d(u64 x) { return __longlong_as_double((long long)(x | 0x4330000000000000ull)) - FP_TWO52; }
+// The magic-number conversion is exact only below 2^52. The reference's NTTStandard / INTTStandard accept any uint64 that
+// does not wrap its lazy arithmetic (lazily accumulated sums, AddLazy / MulCoeffsLazy outputs; ring/ntt.go:174-206 end in
+// a full reduction), so user-supplied words are Barrett-reduced first when a high bit is set (rare, warp-divergent only
+// when it happens).
+__device__ __forceinline__ double u2d_any(u64 x, u64 q, u64 bred_hi) {
+    if (x >> 52) x = bred_add(x, q, bred_hi);
+    return u2d(x);
+}
 // integer-valued 0 <= d < 2^52
 __device__ __forceinline__ u64 d2u(double d) { return (u64)__double_as_longlong(d + FP_TWO52) & 0x000FFFFFFFFFFFFFull; }
 

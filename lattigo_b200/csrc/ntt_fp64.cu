@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) ntt_fp_strided_kernel(FpParams p) {
     double x[R];
     if constexpr (!INVERSE) {
 #pragma unroll
-        for (int k = 0; k < R; k++) x[k] = u2d(in[(size_t)k * stride + l]);
+        for (int k = 0; k < R; k++) x[k] = u2d_any(in[(size_t)k * stride + l], L.q, L.bred_hi);
         const double* tw = L.ftw_fwd;
 #pragma unroll
         for (int u = 0; u < RL; u++) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__((1 << CL) / 16, 2) ntt_fp_chunk_fwd_kernel(FpP
         {   // round 1 from registers: element k of this thread sits at k*T + tid (hi = 0, lo = tid)
             double x[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) x[k] = (s1 > 0) ? __longlong_as_double((long long)raw[k]) : u2d(raw[k]);
+            for (int k = 0; k < 16; k++) x[k] = (s1 > 0) ? __longlong_as_double((long long)raw[k]) : u2d_any(raw[k], L.q, L.bred_hi);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int half = 1 << (3 - u);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__((1 << CL) / 16, 2) ntt_fp_chunk_inv_kernel(FpP
     for (int k = 0; k < 16; k++) {
         const int idx = k * T + tid;
         // inputs are residues < 2q (canonical or lazy); centre them once so that every later bound holds
-        fsm[fpad(idx)] = fp_reduce(u2d(src[idx]), q, qinv);
+        fsm[fpad(idx)] = fp_reduce(u2d_any(src[idx], L.q, L.bred_hi), q, qinv);
     }
     __syncthreads();
     fp_inv_round<CL, R0 + R1, R2, 0>(fsm, nullptr, L, s1, chunk, tid);
