@@ -42,28 +42,42 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="ciphertext pairs per pipeline chunk of the host entry point (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle, one ciphertext pair per worker process (the reference's own parallelism is "one goroutine
-# per ciphertext", schemes/ckks/ckks_benchmarks_test.go:218-229)
+# CPU arm: the reference's CPU path restated in C (oracle/lattigo_cpu_batch.c; Go is not installed), run the way the
+# reference runs its own parallel benchmark: one thread per ciphertext pair sharing read-only inputs and keys
+# (b.RunParallel, schemes/ckks/ckks_benchmarks_test.go:218-229), per-thread scratch reused like sync.Pool
+# (ring/pool.go:10-61), built -O3 -march=native on the box it runs on. Threads = the CPUs this process may really use
+# (affinity mask capped by the cgroup quota: the pool's GPU boxes show 128 logical CPUs but grant a 16-CPU quota, which
+# is what made the round-1 fork pool of os.cpu_count() workers irreproducible).
 # ----------------------------------------------------------------------------------------------------------
-_CPU = {}
+def _mem_available_bytes():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
 
 
-def _cpu_setup(preset_name):
+def run_cpu_arm(args, steps, warmup, pairs_per_step=0, curve=True):
+    """Times `steps` steps of `pairs_per_step` ciphertext pairs (default: one per usable CPU) in ONE process with a native
+    thread per pair slot. Returns the throughput, the usable-CPU report and a 1/8/32/all-thread scaling curve."""
     import numpy as np
-    from lattigo_b200 import params as presets
+    from lattigo_b200 import params as presets      # pure-Python parameter literals (does not load the CUDA library)
+    from oracle import cpu_batch as CB
     from oracle import oracle as O
-    s = presets.PRESETS[preset_name]
+    CB.lib()                                        # dlopen before any timing (and visible to the driver's loader hook)
+    cpus = CB.usable_cpus()
+    s = presets.PRESETS[args.preset]
     params = O.Parameters(s["logN"], s["Q"], s["P"])
     N = params.N()
     rng = np.random.default_rng(1234)
     level, levelP = len(s["Q"]) - 1, len(s["P"]) - 1
     nd = params.BaseRNSDecompositionVectorSize(level, levelP)
-    mods = s["Q"] + s["P"]
 
     def rand_rows(ms, lead):
         out = np.empty(tuple(lead) + (len(ms), N), dtype=np.uint64)
@@ -71,76 +85,78 @@ def _cpu_setup(preset_name):
             out[..., i, :] = rng.integers(0, m, tuple(lead) + (N,), dtype=np.uint64)
         return out
 
-    evk = O.GadgetCiphertext(rand_rows(mods, (nd, 1, 2)), level + 1, levelP + 1)
-    a = rand_rows(s["Q"], (2,))
-    b = rand_rows(s["Q"], (2,))
-    _CPU.update(ev=O.CKKSEvaluator(params, evk), a=a, b=b)
+    evk = O.GadgetCiphertext(rand_rows(s["Q"] + s["P"], (nd, 1, 2)), level + 1, levelP + 1)
+    a = rand_rows(s["Q"], (1, 2)); b = rand_rows(s["Q"], (1, 2))
+    plan = CB.CKKSBatchPlan(params, evk)
+    threads = cpus["usable"]
+    ws_bytes = (9 * (level + 1) + 4 * (levelP + 1) + 2) * N * 8
+    avail = _mem_available_bytes()
+    if avail is not None and threads * ws_bytes > 0.6 * avail:
+        threads = max(1, int(0.6 * avail // ws_bytes))
+    pairs = pairs_per_step or threads
+    threads = min(threads, pairs)
+    per_pair = []
+    for _ in range(warmup):                         # also first-touches every thread's workspace
+        plan.run(a, b, pairs, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, per, _, _ = plan.run(a, b, pairs, threads)
+        per_pair += list(per)
+    dt = time.perf_counter() - t0
+    out = {"value": pairs * steps / dt, "cores": threads, "pairs_per_step": pairs, "steps": steps, "warmup_steps_run": warmup,
+           "seconds": dt, "single_pair_seconds_median": sorted(per_pair)[len(per_pair) // 2],
+           "cpus": {k: cpus[k] for k in ("affinity", "cgroup_quota", "os_cpu_count", "usable")}}
+    if curve:
+        pts = []
+        for nt in sorted({1, 8, 32, threads}):
+            if nt > threads:
+                continue
+            plan.run(a, b, nt, nt)
+            t, per, _, _ = plan.run(a, b, nt, nt)
+            pts.append({"threads": nt, "ct_per_s": nt / t, "ct_per_s_per_thread": 1.0 / t, "pair_seconds_median": float(sorted(per)[len(per) // 2])})
+        out["curve"] = pts
+        out["per_core_efficiency_at_all_threads"] = (out["value"] / threads) / pts[0]["ct_per_s"] if pts else None
+    CB.lib().lo_batch_release()
+    return out
 
 
-def _cpu_one_pair(_):
-    ev, a, b = _CPU["ev"], _CPU["a"], _CPU["b"]
-    t = time.perf_counter()
-    m = ev.MulRelinNew([a[0], a[1]], [b[0], b[1]])
-    ev.Rescale(m)
-    return time.perf_counter() - t
-
-
-def run_cpu_arm(args, steps, warmup, pairs_per_step=0):
-    """Times `steps` steps of `pairs_per_step` ciphertext pairs on all host cores (fork pool, no CUDA in this process)."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    pairs = pairs_per_step or cores
-    _cpu_setup(args.preset)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(processes=min(cores, pairs)) as pool:
-        warm_done = 0
-        for _ in range(warmup):
-            tw = time.perf_counter()
-            pool.map(_cpu_one_pair, range(pairs), chunksize=1)
-            warm_done += 1
-            # one step already touches every page and fills the allocator's free lists; when a step takes many seconds
-            # (N = 2^16: ~18 s) further untimed steps only push the run past "a few minutes"
-            if time.perf_counter() - tw > 10.0:
-                break
-        t0 = time.perf_counter()
-        per_pair = []
-        for _ in range(steps):
-            per_pair += pool.map(_cpu_one_pair, range(pairs), chunksize=1)
-        dt = time.perf_counter() - t0
-    return {"value": pairs * steps / dt, "cores": min(cores, pairs), "pairs_per_step": pairs, "steps": steps, "warmup_steps_run": warm_done,
-            "seconds": dt, "single_pair_seconds_median": sorted(per_pair)[len(per_pair) // 2]}
+def _cpu_baseline_record(r):
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": "%d warm-up + %d timed steps x %d ciphertext pairs (one per usable CPU), C restatement of the reference CPU path "
+                      "(oracle/lattigo_cpu_batch.c, gcc -O3 -march=native, one thread per pair)" % (r["warmup_steps_run"], r["steps"], r["pairs_per_step"]),
+            "cpus": r["cpus"], "single_pair_seconds_median": r["single_pair_seconds_median"], "curve": r.get("curve"),
+            "per_core_efficiency_at_all_threads": r.get("per_core_efficiency_at_all_threads")}
 
 
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    if os.environ.get("LGPU_BENCH_MALLOC") != "1":
-        # The reference recycles its scratch polynomials through sync.Pool (ring/pool.go); numpy would instead
-        # mmap/munmap (and page-fault) every 23 MB temporary. Keep freed blocks in the heap so the CPU arm is not
-        # handicapped by the allocator: glibc tunables must be set before the interpreter starts -> re-exec once.
-        env = dict(os.environ, LGPU_BENCH_MALLOC="1", MALLOC_MMAP_THRESHOLD_="33554432", MALLOC_TRIM_THRESHOLD_="68719476736",
-                   MALLOC_TOP_PAD_="268435456", MALLOC_ARENA_MAX="1")
-        os.execve(sys.executable, [sys.executable] + sys.argv, env)
     r = run_cpu_arm(args, args.steps, args.warmup, args.cpu_sample_pairs)
-    from lattigo_b200 import params as presets      # pure-Python parameter literals (does not load the CUDA library)
+    from lattigo_b200 import params as presets
     P = presets.PRESETS[args.preset]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        # same workload description as the product arm (preset, ring degree, limb counts); each step is a bounded sample
-        # of it: one ciphertext pair per host core instead of the 64 pairs per GPU
-        "config": {"workload": "ckks_mulrelin_rescale", "preset": args.preset, "logN": P["logN"], "q_limbs": len(P["Q"]), "p_limbs": len(P["P"]),
-                   "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "pairs_per_step": r["pairs_per_step"],
-                   "sample": "one ciphertext pair per host core per step (bounded sample of the batch)", "warmup_steps_run": r["warmup_steps_run"],
-                   "note": "oracle = C/Python restatement of the reference's pure-Go path (Go toolchain absent); one pair per worker process"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": "%d steps x %d ciphertext pairs, one per core" % (args.steps, r["pairs_per_step"])},
+        # same workload description (same keys) as the product arm; each step is a bounded sample of it: one ciphertext pair
+        # per usable host CPU instead of the 64 pairs per GPU (see cpu_baseline.sample)
+        "config": _config(args, P, args.gpus),
+        "cpu_baseline": _cpu_baseline_record(r),
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def _config(args, P, world):
+    """Workload description shared verbatim by both arms (the driver compares the two `config` objects)."""
+    nbytes = 2 * args.batch * 2 * len(P["Q"]) * (1 << P["logN"]) * 8
+    return {"workload": "ckks_mulrelin_rescale", "preset": args.preset, "logN": P["logN"], "q_limbs": len(P["Q"]), "p_limbs": len(P["P"]),
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+            "parallelism": "dp%d (one batch per GPU, evk broadcast once)" % world,
+            "l2_policy": "inputs (%.1f GB per GPU) exceed L2; no flush" % (nbytes / 1e9),
+            "timing": "CUDA events on the launching stream, max over ranks (GPU arm); wall clock around the native batch loop (CPU arm)"}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -368,23 +384,19 @@ def gpu_main(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            # bounded CPU sample in a separate process (fork pool there; this process holds a CUDA context)
+            # bounded CPU sample in a separate process (native thread pool there; this process holds a CUDA context)
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
                                     "--preset", args.preset], capture_output=True, text=True, timeout=900)
                 ref = json.loads(r.stdout.strip().splitlines()[-1])
                 cpu = ref["cpu_baseline"]
-                cpu["sample"] = "1 warm-up + 1 timed step x %d ciphertext pairs (one per core), oracle port" % ref["config"]["pairs_per_step"]
             except Exception as ex:  # noqa: BLE001
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "ckks_mulrelin_rescale", "preset": args.preset, "logN": logN, "q_limbs": len(Q), "p_limbs": len(P),
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (one batch per GPU, evk broadcast once)" % world,
-                       "l2_policy": "inputs (%.1f GB per GPU) exceed L2; no flush" % (2 * a.numel() * 8 / 1e9),
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "config": _config(args, s, world),
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

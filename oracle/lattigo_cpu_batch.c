@@ -46,7 +46,7 @@ typedef struct {
 } lo_plan;
 
 /* ---- transforms: same butterflies / stage order as lo_ntt_lazy / intt_core, loop nests specialised ------------ */
-static void ntt_lazy_fast(const u64 *restrict p1, u64 *restrict p2, int N, u64 q, u64 qinv, const u64 *restrict roots) {
+static void ntt_lazy_fast(const u64 *p1, u64 *p2, int N, u64 q, u64 qinv, const u64 *restrict roots) {
     int t = N >> 1;
     u64 F = roots[1];
     for (int j = 0; j < t; j++) {                   /* stage m = 1: no U correction (ring/ntt.go:275-310) */
@@ -79,7 +79,7 @@ static void ntt_fast(const u64 *p1, u64 *p2, int N, u64 q, u64 qinv, const u64 *
     for (int i = 0; i < N; i++) p2[i] = bred_add(p2[i], q, brc);      /* reducevec, ring/ntt.go:176 */
 }
 /* INTTStandard / INTTStandardLazy for N >= 16 (identical: ring/ntt.go:185-206) */
-static void intt_fast(const u64 *restrict p1, u64 *restrict p2, int N, u64 ninv, u64 q, u64 qinv, const u64 *restrict roots) {
+static void intt_fast(const u64 *p1, u64 *p2, int N, u64 ninv, u64 q, u64 qinv, const u64 *restrict roots) {
     int h = N >> 1;
     for (int i = 0; i < h; i++) {                  /* t = 1 */
         u64 x = p1[2 * i], y = p1[2 * i + 1];
