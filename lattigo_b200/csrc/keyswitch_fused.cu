@@ -574,38 +574,6 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
 // >= 4 warps per scheduler issuing it; the 256-thread variant leaves 2 warps per scheduler per CTA and half of them
 // sit in the integer MAC phase or at a barrier.
 // ------------------------------------------------------------------------------------------------------------
-template <int A>
-__device__ __forceinline__ void fp8_load_tw(double (&t)[7], const double* tw, int s1, int chunk, int tid) {
-    constexpr int LOB = 9 - A;
-    const int hi = tid >> LOB;
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-        const int twbase = (1 << (s1 + A + u)) + (chunk << (A + u)) + (hi << u);
-#pragma unroll
-        for (int m = 0; m < (1 << u); m++) t[(1 << u) - 1 + m] = __ldg(tw + twbase + m);
-    }
-}
-template <int A>
-__device__ __forceinline__ void fp8_round(double* sm, const double (&t)[7], double q, double qinv, int tid) {
-    constexpr int LOB = 9 - A;
-    const int hi = tid >> LOB, lo = tid & ((1 << LOB) - 1);
-    const int base = (hi << (12 - A)) + lo;
-    double x[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) x[k] = sm[fpad(base + (k << LOB))];
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-        const int half = 4 >> u;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (k & half) continue;
-            fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], q, qinv);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) sm[fpad(base + (k << LOB))] = x[k];
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // K3, register-MAC variant of the 512 x 8 kernel. The last radix-8 round leaves every thread with 8 CONSECUTIVE
 // coefficients in registers (stages 9..11 act inside aligned groups of 8), so the MAC consumes them right there:
@@ -624,9 +592,6 @@ __device__ __forceinline__ void fp8_round(double* sm, const double (&t)[7], doub
 #ifndef KS_LAZY_X
 #define KS_LAZY_X 1
 #endif
-__device__ __forceinline__ u64 fp_biased_u64(double x, double off52) {
-    return (u64)__double_as_longlong(__dadd_rn(x, off52)) & 0x000FFFFFFFFFFFFFull;
-}
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ u64 mbar_arrive(unsigned bar) {
     u64 tok;

@@ -138,72 +138,6 @@ __global__ void __launch_bounds__(256) ntt_strided_kernel(NttParams p) {
 // ---------------------------------------------------------------------------------------------------
 // chunk pass: global stages [s1, logN) on a contiguous chunk of C = 2^CL elements held in shared memory.
 // ---------------------------------------------------------------------------------------------------
-// One register round of the inverse transform (GS) on chunk-local stages [A, A+RB), processed deepest first.
-template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE, int FAST>
-__device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const LimbConst& L,
-                                          int s1, int chunk, int tid) {
-    const u64 q = L.q, qinv = L.qinv, ninv = L.ninv;
-    const u64* roots = L.roots_bwd;
-    const ulonglong2* twp = L.tw_bwd;
-    const bool lazy = L.inv_lazy != 0;
-    constexpr int G = 16 >> RB;
-    constexpr int RR = 1 << RB;
-    constexpr int LOB = CL - A - RB;
-#pragma unroll
-    for (int gi = 0; gi < G; gi++) {
-        const int g = tid * G + gi;
-        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
-        const int base = (hi << (CL - A)) + lo;
-        u64 x[RR];
-#pragma unroll
-        for (int k = 0; k < RR; k++) x[k] = sm[pad_idx(base + (k << LOB))];
-#pragma unroll
-        for (int u = RB - 1; u >= 0; u--) {
-            const int half = 1 << (RB - 1 - u);
-            const int s = s1 + A + u;
-            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
-            if constexpr (FAST) {
-                // `done` inverse stages precede this one; lazy inputs are < 2^(done+1) q
-                const int done = (CL - 1) - (A + u);
-                if (SCALE && A + u == 0) {
-                    // very last stage of a single-pass transform: fold N^-1, canonical outputs
-                    const u64 addq = lazy ? (q << (done + 1)) : (q << 1);
-#pragma unroll
-                    for (int k = 0; k < RR; k++) {
-                        if (k & half) continue;
-                        const u64 U = x[k], V = x[k + half];
-                        const u64 a = shoup_mul(U + V, L.ninv_s, q);
-                        const u64 c = shoup_mul(U - V + addq, L.last_inv_s, q);
-                        x[k] = a >= q ? a - q : a;
-                        x[k + half] = c >= q ? c - q : c;
-                    }
-                } else {
-                    const u64 addq = lazy ? (q << (done + 1)) : (q << 1);
-#pragma unroll
-                    for (int k = 0; k < RR; k++) {
-                        if (k & half) continue;
-                        const ulonglong2 w = __ldg(twp + twbase + (k >> (RB - u)));
-                        fast_inv_bfly(x[k], x[k + half], w, q, addq, !lazy);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < RR; k++) {
-                    if (k & half) continue;
-                    u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
-                    inv_bfly(x[k], x[k + half], tw, q, qinv);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < RR; k++) {
-            const int idx = base + (k << LOB);
-            if (TO_GLOBAL) gdst[idx] = (SCALE && FAST == 0) ? mred(x[k], ninv, q, qinv) : x[k];
-            else sm[pad_idx(idx)] = x[k];
-        }
-    }
-}
-
 template <int CL, int FAST, int MINB = 1>
 __global__ void __launch_bounds__((1 << CL) >= 16 ? ((1 << CL) / 16) : 1, MINB)
 ntt_chunk_fwd_kernel(NttParams p) {
@@ -378,12 +312,13 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     if (check_common(c, rm, batch)) return -1;
     if (c->ring_type != 0) return launch_ntt_ci(c, rm, false, in, out, batch, mode == NTT_EXACT_LAZY, st);
     RowMap fp, rest;
-    // the FP64 forward chunk pass stores 128 bits at a time
-    const bool vec_ok = aligned16(out.p) && even_words(out.row_stride, out.batch_stride);
+    const bool persist = mode == NTT_CANONICAL && ntt_persist_supported(c);
+    // the two-pass FP64 forward chunk pass stores 128 bits at a time; the persistent kernels use 64-bit accesses only
+    const bool vec_ok = persist || (aligned16(out.p) && even_words(out.row_stride, out.batch_stride));
     if (mode == NTT_CANONICAL && vec_ok && split_rows_fp64(c, rm, fp, rest)) {
         {
-            ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * fp.nrows * batch, c->logN > 12 ? 2 : 1);
-            if (launch_ntt_fp64(c, fp, false, in, out, batch, st)) return -1;
+            ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * fp.nrows * batch, persist ? 1 : (c->logN > 12 ? 2 : 1));
+            if (persist ? launch_ntt_persist(c, fp, false, 0, in, out, batch, st) : launch_ntt_fp64(c, fp, false, in, out, batch, st)) return -1;
         }
         if (rest.nrows == 0) return 0;
         return launch_ntt_int(c, rest, in, out, batch, mode, st);
@@ -397,8 +332,9 @@ int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, i
     RowMap fp, rest;
     if (mode != NTT_REFERENCE_ARITH && split_rows_fp64(c, rm, fp, rest)) {
         {
-            ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * fp.nrows * batch, c->logN > 12 ? 2 : 1);
-            if (launch_ntt_fp64(c, fp, true, in, out, batch, st)) return -1;
+            const bool persist = ntt_persist_supported(c);
+            ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * fp.nrows * batch, persist ? 1 : (c->logN > 12 ? 2 : 1));
+            if (persist ? launch_ntt_persist(c, fp, true, 0, in, out, batch, st) : launch_ntt_fp64(c, fp, true, in, out, batch, st)) return -1;
         }
         if (rest.nrows == 0) return 0;
         return launch_intt_int(c, rest, in, out, batch, mode, st);
@@ -414,8 +350,10 @@ static int launch_ntt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, in
     p.logN = c->logN; p.mode = mode; p.ci = 0;
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
-    ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * rm.nrows * batch, s1 > 0 ? 2 : 1);
     const int fast = (mode == NTT_CANONICAL) ? fast_variant(c, rm, false) : 0;
+    const bool persist = fast != 0 && ntt_persist_supported(c);
+    ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * rm.nrows * batch, (s1 > 0 && !persist) ? 2 : 1);
+    if (persist) return launch_ntt_persist(c, rm, false, fast, in, out, batch, st);
     if (s1 > 0) {
         int rc = fast == 2 ? launch_strided<false, 2>(s1, p, rm.nrows, batch, st)
                : fast == 1 ? launch_strided<false, 1>(s1, p, rm.nrows, batch, st)
@@ -437,7 +375,9 @@ static int launch_intt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, i
     p.logN = c->logN; p.mode = mode; p.ci = 0;
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
-    ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * rm.nrows * batch, s1 > 0 ? 2 : 1);
+    const bool persist = fast != 0 && ntt_persist_supported(c);
+    ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * rm.nrows * batch, (s1 > 0 && !persist) ? 2 : 1);
+    if (persist) return launch_ntt_persist(c, rm, true, fast, in, out, batch, st);
     dim3 grid(1u << s1, rm.nrows, batch);
     if (launch_chunk_dyn(cl, true, fast, p, grid, st)) return -1;
     if (s1 > 0) {

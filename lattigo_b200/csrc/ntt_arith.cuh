@@ -142,7 +142,7 @@ __device__ __forceinline__ void fwd_round(u64* sm, const u64* gsrc, const LimbCo
 #pragma unroll
         for (int k = 0; k < RR; k++) {
             const int idx = base + (k << LOB);
-            x[k] = FROM_GLOBAL ? gsrc[idx] : sm[pad_idx(idx)];
+            x[k] = FROM_GLOBAL ? __ldcg(gsrc + idx) : sm[pad_idx(idx)];
         }
 #pragma unroll
         for (int u = 0; u < RB; u++) {
@@ -192,8 +192,8 @@ __device__ __forceinline__ void fp_fwd_round(double* sm, const u64* gsrc, const 
 #pragma unroll
         for (int k = 0; k < RR; k++) {
             const int idx = base + (k << LOB);
-            if (SRC == 1) x[k] = u2d(gsrc[idx]);
-            else if (SRC == 2) x[k] = __longlong_as_double((long long)gsrc[idx]);
+            if (SRC == 1) x[k] = u2d(__ldcg(gsrc + idx));
+            else if (SRC == 2) x[k] = __longlong_as_double((long long)__ldcg(gsrc + idx));
             else x[k] = sm[fpad(idx)];
         }
 #pragma unroll
@@ -278,6 +278,163 @@ __device__ __forceinline__ void fp_fwd_round_tw_out(const double* sm, const doub
         for (int k = 0; k < RR; k += 2)
             *reinterpret_cast<ulonglong2*>(gdst + base + k) = make_ulonglong2(fp_canon(x[k], q, qinv), fp_canon(x[k + 1], q, qinv));
     }
+}
+
+
+// ---- moved here so that the persistent transform kernels (ntt_persist.cu) share them ---------------------------------
+// One register round of the inverse transform (GS) on chunk-local stages [A, A+RB), processed deepest first.
+template <int CL, int A, int RB, bool TO_GLOBAL, bool SCALE, int FAST>
+__device__ __forceinline__ void inv_round(u64* sm, u64* gdst, const LimbConst& L,
+                                          int s1, int chunk, int tid) {
+    const u64 q = L.q, qinv = L.qinv, ninv = L.ninv;
+    const u64* roots = L.roots_bwd;
+    const ulonglong2* twp = L.tw_bwd;
+    const bool lazy = L.inv_lazy != 0;
+    constexpr int G = 16 >> RB;
+    constexpr int RR = 1 << RB;
+    constexpr int LOB = CL - A - RB;
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int g = tid * G + gi;
+        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
+        const int base = (hi << (CL - A)) + lo;
+        u64 x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) x[k] = sm[pad_idx(base + (k << LOB))];
+#pragma unroll
+        for (int u = RB - 1; u >= 0; u--) {
+            const int half = 1 << (RB - 1 - u);
+            const int s = s1 + A + u;
+            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+            if constexpr (FAST) {
+                // `done` inverse stages precede this one; lazy inputs are < 2^(done+1) q
+                const int done = (CL - 1) - (A + u);
+                if (SCALE && A + u == 0) {
+                    // very last stage of a single-pass transform: fold N^-1, canonical outputs
+                    const u64 addq = lazy ? (q << (done + 1)) : (q << 1);
+#pragma unroll
+                    for (int k = 0; k < RR; k++) {
+                        if (k & half) continue;
+                        const u64 U = x[k], V = x[k + half];
+                        const u64 a = shoup_mul(U + V, L.ninv_s, q);
+                        const u64 c = shoup_mul(U - V + addq, L.last_inv_s, q);
+                        x[k] = a >= q ? a - q : a;
+                        x[k + half] = c >= q ? c - q : c;
+                    }
+                } else {
+                    const u64 addq = lazy ? (q << (done + 1)) : (q << 1);
+#pragma unroll
+                    for (int k = 0; k < RR; k++) {
+                        if (k & half) continue;
+                        const ulonglong2 w = __ldg(twp + twbase + (k >> (RB - u)));
+                        fast_inv_bfly(x[k], x[k + half], w, q, addq, !lazy);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    u64 tw = __ldg(roots + twbase + (k >> (RB - u)));
+                    inv_bfly(x[k], x[k + half], tw, q, qinv);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k++) {
+            const int idx = base + (k << LOB);
+            if (TO_GLOBAL) gdst[idx] = (SCALE && FAST == 0) ? mred(x[k], ninv, q, qinv) : x[k];
+            else sm[pad_idx(idx)] = x[k];
+        }
+    }
+}
+
+
+// inverse round over chunk-local stages [A, A+RB), deepest first; inputs |x| < 0.66q; DST: 0 smem (renormalised),
+// 1 global raw doubles (renormalised), 2 global canonical u64 with N^-1 folded into the last stage (single pass)
+template <int CL, int A, int RB, int DST>
+__device__ __forceinline__ void fp_inv_round(double* sm, u64* gdst, const LimbConst& L, int s1, int chunk, int tid) {
+    constexpr int G = 16 >> RB, RR = 1 << RB, LOB = CL - A - RB;
+    const double q = L.fq, qinv = L.fqinv;
+    const double* tw = L.ftw_bwd;
+#pragma unroll
+    for (int gi = 0; gi < G; gi++) {
+        const int g = tid * G + gi;
+        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
+        const int base = (hi << (CL - A)) + lo;
+        double x[RR];
+#pragma unroll
+        for (int k = 0; k < RR; k++) x[k] = sm[fpad(base + (k << LOB))];
+#pragma unroll
+        for (int u = RB - 1; u >= 0; u--) {
+            const int half = 1 << (RB - 1 - u);
+            const int s = s1 + A + u;
+            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
+            if (DST == 2 && A + u == 0) {
+#pragma unroll
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    const double a = x[k], c = x[k + half];
+                    x[k] = fp_mulmod(__dadd_rn(a, c), L.fninv, q, qinv);
+                    x[k + half] = fp_mulmod(__dadd_rn(a, -c), L.flast_inv, q, qinv);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RR; k++) {
+                    if (k & half) continue;
+                    fp_inv_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (RB - u))), q, qinv);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RR; k++) {
+            const int idx = base + (k << LOB);
+            if (DST == 2) gdst[idx] = d2u(x[k] < 0.0 ? x[k] + q : x[k]);
+            else {
+                const double r = fp_reduce(x[k], q, qinv);     // sums grew up to 2^RB * 0.66q: renormalise once per round
+                if (DST == 1) gdst[idx] = (u64)__double_as_longlong(r);
+                else sm[fpad(idx)] = r;
+            }
+        }
+    }
+}
+
+
+// 512-thread x 8-element FP64 rounds (four radix-8 rounds per 4096-element chunk)
+template <int A>
+__device__ __forceinline__ void fp8_load_tw(double (&t)[7], const double* tw, int s1, int chunk, int tid) {
+    constexpr int LOB = 9 - A;
+    const int hi = tid >> LOB;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int twbase = (1 << (s1 + A + u)) + (chunk << (A + u)) + (hi << u);
+#pragma unroll
+        for (int m = 0; m < (1 << u); m++) t[(1 << u) - 1 + m] = __ldg(tw + twbase + m);
+    }
+}
+template <int A>
+__device__ __forceinline__ void fp8_round(double* sm, const double (&t)[7], double q, double qinv, int tid) {
+    constexpr int LOB = 9 - A;
+    const int hi = tid >> LOB, lo = tid & ((1 << LOB) - 1);
+    const int base = (hi << (12 - A)) + lo;
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = sm[fpad(base + (k << LOB))];
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int half = 4 >> u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k & half) continue;
+            fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], q, qinv);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) sm[fpad(base + (k << LOB))] = x[k];
+}
+
+
+__device__ __forceinline__ u64 fp_biased_u64(double x, double off52) {
+    return (u64)__double_as_longlong(__dadd_rn(x, off52)) & 0x000FFFFFFFFFFFFFull;
 }
 
 

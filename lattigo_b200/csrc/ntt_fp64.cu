@@ -91,55 +91,6 @@ __global__ void __launch_bounds__(256) ntt_fp_strided_kernel(FpParams p) {
 }
 
 // ---- chunk pass ------------------------------------------------------------------------------------------
-// inverse round over chunk-local stages [A, A+RB), deepest first; inputs |x| < 0.66q; DST: 0 smem (renormalised),
-// 1 global raw doubles (renormalised), 2 global canonical u64 with N^-1 folded into the last stage (single pass)
-template <int CL, int A, int RB, int DST>
-__device__ __forceinline__ void fp_inv_round(double* sm, u64* gdst, const LimbConst& L, int s1, int chunk, int tid) {
-    constexpr int G = 16 >> RB, RR = 1 << RB, LOB = CL - A - RB;
-    const double q = L.fq, qinv = L.fqinv;
-    const double* tw = L.ftw_bwd;
-#pragma unroll
-    for (int gi = 0; gi < G; gi++) {
-        const int g = tid * G + gi;
-        const int hi = g >> LOB, lo = g & ((1 << LOB) - 1);
-        const int base = (hi << (CL - A)) + lo;
-        double x[RR];
-#pragma unroll
-        for (int k = 0; k < RR; k++) x[k] = sm[fpad(base + (k << LOB))];
-#pragma unroll
-        for (int u = RB - 1; u >= 0; u--) {
-            const int half = 1 << (RB - 1 - u);
-            const int s = s1 + A + u;
-            const int twbase = (1 << s) + (chunk << (A + u)) + (hi << u);
-            if (DST == 2 && A + u == 0) {
-#pragma unroll
-                for (int k = 0; k < RR; k++) {
-                    if (k & half) continue;
-                    const double a = x[k], c = x[k + half];
-                    x[k] = fp_mulmod(__dadd_rn(a, c), L.fninv, q, qinv);
-                    x[k + half] = fp_mulmod(__dadd_rn(a, -c), L.flast_inv, q, qinv);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < RR; k++) {
-                    if (k & half) continue;
-                    fp_inv_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (RB - u))), q, qinv);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < RR; k++) {
-            const int idx = base + (k << LOB);
-            if (DST == 2) gdst[idx] = d2u(x[k] < 0.0 ? x[k] + q : x[k]);
-            else {
-                const double r = fp_reduce(x[k], q, qinv);     // sums grew up to 2^RB * 0.66q: renormalise once per round
-                if (DST == 1) gdst[idx] = (u64)__double_as_longlong(r);
-                else sm[fpad(idx)] = r;
-            }
-        }
-    }
-}
-
 // Forward chunk pass. One CTA owns a (limb, chunk) pair and walks over `bpc` batch elements: the twiddles of that
 // pair stay in L1, and the next element's 16 values per thread are prefetched into registers while the current
 // element is in its second and third rounds, so the round-one global-load latency is hidden.
