@@ -327,8 +327,8 @@ def gpu_main(args):
         except Exception:
             pass
         # standalone transform rate (BASELINE metric "NTT GB/s vs roofline"): Ring.NTT on all Q limbs of the preset,
-        # 8 polynomials per launch (184 MB in + 184 MB out > L2), CUDA events around `iters` launches
-        xs = rand_rows(Q, (8,)); ys = torch.empty_like(xs)
+        # 16 polynomials per launch (369 MB in + 369 MB out > L2), CUDA events around `iters` launches
+        xs = rand_rows(Q, (16,)); ys = torch.empty_like(xs)
         rq = ctx.ringQ
         for _ in range(3):
             rq.NTT(xs, ys)
@@ -340,9 +340,9 @@ def gpu_main(args):
             rq.NTT(xs, ys)
         eb.record(); torch.cuda.synchronize()
         t_ntt = ea.elapsed_time(eb) * 1e-3 / iters
-        ntt_bytes = 16.0 * N * len(Q) * 8
-        ntt_standalone = {"op": "Ring.NTT, %d limbs x 8 polynomials, N=2^%d" % (len(Q), logN), "us_per_launch": t_ntt * 1e6,
-                          "us_per_limb_transform": t_ntt * 1e6 / (len(Q) * 8), "alg_bytes_per_launch": ntt_bytes,
+        ntt_bytes = 16.0 * N * len(Q) * 16
+        ntt_standalone = {"op": "Ring.NTT, %d limbs x 16 polynomials, N=2^%d" % (len(Q), logN), "us_per_launch": t_ntt * 1e6,
+                          "us_per_limb_transform": t_ntt * 1e6 / (len(Q) * 16), "alg_bytes_per_launch": ntt_bytes,
                           "achieved": ntt_bytes / t_ntt / 1e9, "unit": "GB/s", "frac": ntt_bytes / t_ntt / 1e9 / peak}
         del xs, ys
         roof = {"bound": "hbm", "kernel": kernel_names.get(names[dom], names[dom]), "kernel_class": names[dom],

@@ -167,7 +167,7 @@ int launch_ntt_ci(const Ctx* c, const RowMap& rm, bool inverse, CSpan in, Span o
 int launch_ntt_fp64(const Ctx* c, const RowMap& rm, bool inverse, CSpan in, Span out, int batch, cudaStream_t st);
 
 // ntt_persist.cu: single-launch, single-HBM-pass transforms (2^13 <= N <= 2^16); kind 0 = FP64-pipe rows, 1 / 2 = integer rows
-bool ntt_persist_supported(const Ctx* c);
+bool ntt_persist_supported(const Ctx* c, bool inverse);
 int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, CSpan in, Span out, int batch, cudaStream_t st);
 
 // basisext.cu

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
     __shared__ __align__(8) u64 s_bar;
     double* fsm = reinterpret_cast<double*>(smem);
     // accumulators: component c, pair j (coefficients 8*tid + 2j, 2j+1) at acc + ((c*4 + j) * T + tid) * 2
-    ulonglong2* accs = reinterpret_cast<ulonglong2*>(smem + 4096 + 256 + 8);
+    ulonglong2* accs = reinterpret_cast<ulonglong2*>(smem + 4096);       // the transform tile is XOR-swizzled, not padded
     const int b = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
     const int limb = p.rm.limb[blockIdx.z];
     const int row = p.rm.drow[blockIdx.z];
@@ -666,34 +666,23 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                     }
                 }
                 if (pending) { mbar_wait(bar, tok); pending = false; }
-#pragma unroll
-                for (int k = 0; k < 8; k++) fsm[fpad(k * T + tid)] = x[k];
+                fp8s_store_r1(fsm, x, tid);
             }
             double t[7];
             fp8_load_tw<3>(t, tw, s1, chunk, tid);
             __syncthreads();
-            fp8_round<3>(fsm, t, fq, fqinv, tid);
+            fp8s_round2(fsm, t, fq, fqinv, tid);
             fp8_load_tw<6>(t, tw, s1, chunk, tid);
-            __syncthreads();
-            fp8_round<6>(fsm, t, fq, fqinv, tid);
+            fp8s_pair_sync(tid);
+            fp8s_round3(fsm, t, fq, fqinv, tid);
             fp8_load_tw<9>(t, tw, s1, chunk, tid);
-            __syncthreads();
+            __syncwarp();
             {   // last round stays in registers: coefficients 8*tid .. 8*tid+7
                 double x[8];
-                const int base = tid << 3;
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = fsm[fpad(base + k)];
+                fp8s_load_r4(fsm, x, tid);
                 tok = mbar_arrive(bar);
                 pending = true;
-#pragma unroll
-                for (int u = 0; u < 3; u++) {
-                    const int half = 4 >> u;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        if (k & half) continue;
-                        fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], fq, fqinv);
-                    }
-                }
+                fp8_bflys(x, t, fq, fqinv);
 #pragma unroll
                 for (int k = 0; k < 8; k++) xv[k] = KS_LAZY_X ? fp_biased_u64(x[k], off52) : fp_canon(x[k], fq, fqinv);
             }
@@ -1019,41 +1008,28 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
                 fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), fq, fqinv);
             }
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++) fsm[fpad(k * T + tid)] = x[k];
+        fp8s_store_r1(fsm, x, tid);
     }
     double t[7];
     fp8_load_tw<3>(t, tw, s1, chunk, tid);
     __syncthreads();
-    fp8_round<3>(fsm, t, fq, fqinv, tid);
+    fp8s_round2(fsm, t, fq, fqinv, tid);
     fp8_load_tw<6>(t, tw, s1, chunk, tid);
-    __syncthreads();
-    fp8_round<6>(fsm, t, fq, fqinv, tid);
+    fp8s_pair_sync(tid);
+    fp8s_round3(fsm, t, fq, fqinv, tid);
     fp8_load_tw<9>(t, tw, s1, chunk, tid);
     // the operands of the epilogue for this thread's 8 consecutive coefficients (last round: stages 9..11 act inside
-    // aligned groups of 8), issued before the barrier so that their latency overlaps the wait
+    // aligned groups of 8), issued before the warp-level exchange so that their latency overlaps it
     ulonglong2 a[4], d[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         a[j] = *reinterpret_cast<const ulonglong2*>(A + 8 * tid + 2 * j);
         d[j] = D ? *reinterpret_cast<const ulonglong2*>(D + 8 * tid + 2 * j) : make_ulonglong2(0, 0);
     }
-    __syncthreads();
+    __syncwarp();
     double x[8];
-    {
-        const int base = tid << 3;
-#pragma unroll
-        for (int k = 0; k < 8; k++) x[k] = fsm[fpad(base + k)];
-#pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const int half = 4 >> u;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (k & half) continue;
-                fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], fq, fqinv);
-            }
-        }
-    }
+    fp8s_load_r4(fsm, x, tid);
+    fp8_bflys(x, t, fq, fqinv);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         ulonglong2 r;

@@ -312,7 +312,7 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     if (check_common(c, rm, batch)) return -1;
     if (c->ring_type != 0) return launch_ntt_ci(c, rm, false, in, out, batch, mode == NTT_EXACT_LAZY, st);
     RowMap fp, rest;
-    const bool persist = mode == NTT_CANONICAL && ntt_persist_supported(c);
+    const bool persist = mode == NTT_CANONICAL && ntt_persist_supported(c, false);
     // the two-pass FP64 forward chunk pass stores 128 bits at a time; the persistent kernels use 64-bit accesses only
     const bool vec_ok = persist || (aligned16(out.p) && even_words(out.row_stride, out.batch_stride));
     if (mode == NTT_CANONICAL && vec_ok && split_rows_fp64(c, rm, fp, rest)) {
@@ -332,7 +332,7 @@ int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, i
     RowMap fp, rest;
     if (mode != NTT_REFERENCE_ARITH && split_rows_fp64(c, rm, fp, rest)) {
         {
-            const bool persist = ntt_persist_supported(c);
+            const bool persist = ntt_persist_supported(c, true);
             ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * fp.nrows * batch, persist ? 1 : (c->logN > 12 ? 2 : 1));
             if (persist ? launch_ntt_persist(c, fp, true, 0, in, out, batch, st) : launch_ntt_fp64(c, fp, true, in, out, batch, st)) return -1;
         }
@@ -351,7 +351,7 @@ static int launch_ntt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, in
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
     const int fast = (mode == NTT_CANONICAL) ? fast_variant(c, rm, false) : 0;
-    const bool persist = fast != 0 && ntt_persist_supported(c);
+    const bool persist = fast != 0 && ntt_persist_supported(c, false);
     ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * rm.nrows * batch, (s1 > 0 && !persist) ? 2 : 1);
     if (persist) return launch_ntt_persist(c, rm, false, fast, in, out, batch, st);
     if (s1 > 0) {
@@ -375,7 +375,7 @@ static int launch_intt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, i
     p.logN = c->logN; p.mode = mode; p.ci = 0;
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
-    const bool persist = fast != 0 && ntt_persist_supported(c);
+    const bool persist = fast != 0 && ntt_persist_supported(c, true);
     ProfScope ps(LGPU_KCLASS_NTT_INV, st, 16.0 * c->N * rm.nrows * batch, (s1 > 0 && !persist) ? 2 : 1);
     if (persist) return launch_ntt_persist(c, rm, true, fast, in, out, batch, st);
     dim3 grid(1u << s1, rm.nrows, batch);

@@ -438,4 +438,67 @@ __device__ __forceinline__ u64 fp_biased_u64(double x, double off52) {
 }
 
 
+__device__ __forceinline__ int swz(int i) { return i ^ (((i >> 4) & 3) << 1) ^ (((i >> 6) & 1) * 9); }
+
+// swz is GF(2)-linear, so swz(base + (k << s)) = swz(base) ^ swz(k << s) whenever base has no bits where k << s has:
+// the k-dependent part is a compile-time constant and each round needs at most 8 address registers per thread
+// (computed once, used for the loads and the stores) instead of a shift / xor / select chain per access.
+__host__ __device__ constexpr int swzc(int i) { return i ^ (((i >> 4) & 3) << 1) ^ (((i >> 6) & 1) * 9); }
+
+__device__ __forceinline__ void fp8_bflys(double (&x)[8], const double (&t)[7], double q, double qinv) {
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int half = 4 >> u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k & half) continue;
+            fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], q, qinv);
+        }
+    }
+}
+
+
+// The four radix-8 rounds of a 4096-element chunk on a swizzled tile (512 threads x 8 elements). Round 1 is done by the
+// caller from registers; its results are stored with fp8s_store_r1 and followed by a CTA barrier. Round 2 works inside
+// 512-element groups (one pair of warps: fp8s_pair_sync), rounds 3 and 4 inside one warp's 256 elements (__syncwarp).
+__device__ __forceinline__ void fp8s_store_r1(double* fsm, const double (&x)[8], int tid) {
+    double* a = fsm + swz(tid);                            // swz(tid + 512 k) = swz(tid) + 512 k
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[512 * k] = x[k];
+}
+__device__ __forceinline__ void fp8s_round2(double* fsm, const double (&tt)[7], double q, double qinv, int tid) {
+    // base = hi * 512 + lo, elements base + 64 k; swzc(64 k) = 64 k ^ ((k & 1) * 9)
+    const int tb = swz(((tid >> 6) << 9) + (tid & 63));
+    double* a0 = fsm + tb;
+    double* a1 = fsm + (tb ^ 9);
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = ((k & 1) ? a1 : a0)[64 * k];
+    fp8_bflys(x, tt, q, qinv);
+#pragma unroll
+    for (int k = 0; k < 8; k++) ((k & 1) ? a1 : a0)[64 * k] = x[k];
+}
+__device__ __forceinline__ void fp8s_pair_sync(int tid) {
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (tid >> 6)) : "memory");          // the two warps of one 512-element group
+}
+__device__ __forceinline__ void fp8s_round3(double* fsm, const double (&tt)[7], double q, double qinv, int tid) {
+    // base = hi * 64 + lo, elements base + 8 k; swzc(8 k) = 8 k ^ ((k >> 1) << 1)
+    const int tb = swz(((tid >> 3) << 6) + (tid & 7));
+    double* a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = fsm + ((tb ^ ((k & 1) << 3) ^ ((k >> 1) << 1)) + ((k >> 1) << 4));
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = *a[k];
+    fp8_bflys(x, tt, q, qinv);
+#pragma unroll
+    for (int k = 0; k < 8; k++) *a[k] = x[k];
+}
+// round 4 operands: elements 8 tid + k live at swz(8 tid) ^ k
+__device__ __forceinline__ void fp8s_load_r4(const double* fsm, double (&x)[8], int tid) {
+    const int tb = swz(tid << 3);
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = fsm[tb ^ k];
+}
+
 }  // namespace lgpu

@@ -200,25 +200,6 @@ struct FpFwdOps {
 //     of warps (named barrier, 64 threads), round 3 -> 4 and the copy-out inside one warp's 256 consecutive elements
 //     (__syncwarp): warps drift apart and the FP64 phases of some overlap the exchange phases of others.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int swz(int i) { return i ^ (((i >> 4) & 3) << 1) ^ (((i >> 6) & 1) * 9); }
-
-// swz is GF(2)-linear, so swz(base + (k << s)) = swz(base) ^ swz(k << s) whenever base has no bits where k << s has:
-// the k-dependent part is a compile-time constant and each round needs at most 8 address registers per thread
-// (computed once, used for the loads and the stores) instead of a shift / xor / select chain per access.
-__host__ __device__ constexpr int swzc(int i) { return i ^ (((i >> 4) & 3) << 1) ^ (((i >> 6) & 1) * 9); }
-
-__device__ __forceinline__ void fp8_bflys(double (&x)[8], const double (&t)[7], double q, double qinv) {
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-        const int half = 4 >> u;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (k & half) continue;
-            fp_fwd_bfly(x[k], x[k + half], t[(1 << u) - 1 + (k >> (3 - u))], q, qinv);
-        }
-    }
-}
-
 template <int RL>
 struct FpFwdOps2 : FpFwdOps<RL, 0> {
     static constexpr int T = 512;
@@ -260,56 +241,56 @@ struct FpFwdOps2 : FpFwdOps<RL, 0> {
         for (int k = 0; k < R; k++) t.out[(size_t)k * stride + l] = (u64)__double_as_longlong(x[k]);
     }
 
-    static __device__ __forceinline__ void pass2(const PersistParams& p, int lt, int chunk, u64* smem) {
+    // round 1 (stages 0..2 of the chunk): element k of this thread = k * 512 + tid. SRC 0: straight from L2 (ld.global.cg);
+    // SRC 1: from the tile itself, where a bulk-async copy (TMA) landed the chunk linearly -- the swizzled store goes to
+    // words of the same 16-word group, i.e. words read by lanes of the same half-warp, hence the __syncwarp.
+    template <int SRC>
+    static __device__ __forceinline__ void round1(const LimbConst& L, const u64* io, u64* smem, int chunk, int tid) {
         constexpr int s1 = RL;
-        const int tid = threadIdx.x;
-        const TileRef t = tile_ref(p, lt);
-        const LimbConst& L = p.limbs[t.limb];
         double* fsm = reinterpret_cast<double*>(smem);
         const double fq = L.fq, fqinv = L.fqinv;
         const double* tw = L.ftw_fwd;
-        u64* io = t.out + ((size_t)chunk << 12);
         double tt[7];
-        {   // round 1 (stages 0..2 of the chunk): element k of this thread = k * 512 + tid, straight from L2
 #pragma unroll
-            for (int u = 0; u < 3; u++)
+        for (int u = 0; u < 3; u++)
 #pragma unroll
-                for (int m = 0; m < (1 << u); m++) tt[(1 << u) - 1 + m] = __ldg(tw + (1 << (s1 + u)) + (chunk << u) + m);
-            double x[8];
+            for (int m = 0; m < (1 << u); m++) tt[(1 << u) - 1 + m] = __ldg(tw + (1 << (s1 + u)) + (chunk << u) + m);
+        double x[8];
+        if (SRC == 0) {
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)__ldcg(io + k * T + tid));
-            fp8_bflys(x, tt, fq, fqinv);
-            double* a = fsm + swz(tid);                        // swz(tid + 512 k) = swz(tid) + 512 k
+        } else {
 #pragma unroll
-            for (int k = 0; k < 8; k++) a[512 * k] = x[k];
+            for (int k = 0; k < 8; k++) x[k] = fsm[k * T + tid];
+            __syncwarp();
         }
-        fp8_load_tw<3>(tt, tw, s1, chunk, tid);
+        fp8_bflys(x, tt, fq, fqinv);
+        double* a = fsm + swz(tid);                        // swz(tid + 512 k) = swz(tid) + 512 k
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[512 * k] = x[k];
+    }
+
+    static __device__ __forceinline__ void pass2(const PersistParams& p, int lt, int chunk, u64* smem) {
+        const TileRef t = tile_ref(p, lt);
+        const LimbConst& L = p.limbs[t.limb];
+        u64* io = t.out + ((size_t)chunk << 12);
+        round1<0>(L, io, smem, chunk, threadIdx.x);
         __syncthreads();
-        {   // round 2 (stages 3..5): base = hi * 512 + lo, elements base + 64 k; swzc(64 k) = 64 k ^ ((k & 1) * 9)
-            const int tb = swz(((tid >> 6) << 9) + (tid & 63));
-            double* a0 = fsm + tb;
-            double* a1 = fsm + (tb ^ 9);
-            double x[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = ((k & 1) ? a1 : a0)[64 * k];
-            fp8_bflys(x, tt, fq, fqinv);
-#pragma unroll
-            for (int k = 0; k < 8; k++) ((k & 1) ? a1 : a0)[64 * k] = x[k];
-        }
+        tail(p, L, io, smem, chunk, threadIdx.x);
+    }
+
+    // rounds 2..4 and the copy-out; the caller has issued the CTA barrier that follows round 1
+    static __device__ __forceinline__ void tail(const PersistParams& p, const LimbConst& L, u64* io, u64* smem, int chunk, int tid) {
+        constexpr int s1 = RL;
+        double* fsm = reinterpret_cast<double*>(smem);
+        const double fq = L.fq, fqinv = L.fqinv;
+        const double* tw = L.ftw_fwd;
+        double tt[7];
+        fp8_load_tw<3>(tt, tw, s1, chunk, tid);
+        fp8s_round2(fsm, tt, fq, fqinv, tid);              // stages 3..5
         fp8_load_tw<6>(tt, tw, s1, chunk, tid);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + (tid >> 6)) : "memory");      // the two warps of one 512-element group
-        {   // round 3 (stages 6..8): base = hi * 64 + lo, elements base + 8 k; swzc(8 k) = 8 k ^ ((k >> 1) << 1)
-            const int tb = swz(((tid >> 3) << 6) + (tid & 7));
-            double* a[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) a[k] = fsm + ((tb ^ ((k & 1) << 3) ^ ((k >> 1) << 1)) + ((k >> 1) << 4));
-            double x[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) x[k] = *a[k];
-            fp8_bflys(x, tt, fq, fqinv);
-#pragma unroll
-            for (int k = 0; k < 8; k++) *a[k] = x[k];
-        }
+        fp8s_pair_sync(tid);
+        fp8s_round3(fsm, tt, fq, fqinv, tid);              // stages 6..8
         fp8_load_tw<9>(tt, tw, s1, chunk, tid);
         __syncwarp();
         {   // round 4 (stages 9..11): elements 8 tid + k -> swz(8 tid) ^ k; canonical residues go back to the same words
@@ -614,6 +595,148 @@ __global__ void __launch_bounds__(Ops::T, Ops::MINB) ntt_persist2_kernel(Persist
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Third-generation loop, forward FP64 only: the chunk of the NEXT pass-2 tile is brought from L2 into the other half of a
+// double-buffered tile by ONE bulk-async copy (cp.async.bulk = TMA, 32 KB, completion on an mbarrier) issued by thread 0
+// as soon as the next ticket is known and its pass-1 tiles are published -- the L2 round trip that opened every pass-2
+// tile (8 dependent-free LDG per thread, then nothing to do until they return) disappears behind the current tile.
+// Round 1 then reads the landed chunk from shared memory. Needs 16-byte aligned rows (p.tma), else round 1 loads directly.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+template <int RL>
+__global__ void __launch_bounds__(512, 2) ntt_persist_tma_kernel(PersistParams p, int tma_ok) {
+    using Ops = FpFwdOps2<RL>;
+    constexpr int T = 512;
+    extern __shared__ __align__(1024) u64 psm[];          // two 4096-word tiles
+    __shared__ __align__(8) u64 s_mbar[2];
+    __shared__ int s_next[2], s_land[2];
+    const int per = p.n1 + p.n2;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_next[0] = (int)atomicAdd(p.ctr, 1u);
+        s_land[0] = 0;
+    }
+    __syncthreads();
+    unsigned phase[2] = {0u, 0u};
+    int par = 0;
+    for (;;) {
+        const int t = s_next[par];
+        const int landed = s_land[par];
+        if (t >= p.total) break;
+        unsigned nxt = 0;
+        if (tid == 0) nxt = atomicAdd(p.ctr, 1u);
+        const int s = t / per, j = t - s * per;
+        u64* buf = psm + par * 4096;
+        // thread 0: publish the next ticket; if it is a pass-2 tile whose pass-1 tiles are done, start its bulk copy now
+        auto publish = [&]() {
+            const int tn = (int)nxt;
+            int land = 0;
+            if (tn < p.total && tma_ok) {
+                const int sn = tn / per, jn = tn - sn * per;
+                const int ltn = sn - p.D;
+                if (jn >= p.n1 && ltn >= 0 && ld_acquire_u32(p.ctr + 1 + ltn) >= (unsigned)p.n1) {
+                    const TileRef tr = tile_ref(p, ltn);
+                    const u64* src = tr.out + ((size_t)(jn - p.n1) << 12);
+                    const unsigned dst = smem_u32(psm + (par ^ 1) * 4096), bar = smem_u32(&s_mbar[par ^ 1]);
+                    asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores of the producers -> async-proxy read
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32768u) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(src), "r"(32768u), "r"(bar) : "memory");
+                    land = 1;
+                }
+            }
+            s_next[par ^ 1] = tn;
+            s_land[par ^ 1] = land;
+        };
+        int lt1 = -1;
+        bool done_publish = false;
+        if (j < p.n1) {
+            if (s < p.nLT) { Ops::pass1(p, s, j, buf); lt1 = s; }
+        } else {
+            const int lt = s - p.D;
+            if (lt >= 0) {
+                const int chunk = j - p.n1;
+                const TileRef tr = tile_ref(p, lt);
+                const LimbConst& L = p.limbs[tr.limb];
+                u64* io = tr.out + ((size_t)chunk << 12);
+                if (landed) {
+                    mbar_wait_parity(smem_u32(&s_mbar[par]), phase[par]);
+                    phase[par] ^= 1u;
+                    Ops::template round1<1>(L, io, buf, chunk, tid);
+                } else {
+                    const unsigned* c = p.ctr + 1 + lt;
+                    while (ld_acquire_u32(c) < (unsigned)p.n1) __nanosleep(64);
+                    Ops::template round1<0>(L, io, buf, chunk, tid);
+                }
+                if (tid == 0) publish();
+                done_publish = true;
+                __syncthreads();
+                Ops::tail(p, L, io, buf, chunk, tid);
+            }
+        }
+        if (!done_publish && tid == 0) publish();
+        __syncthreads();
+        if (lt1 >= 0 && tid == 0) {
+            __threadfence();
+            atomicAdd(p.ctr + 1 + lt1, 1u);
+        }
+        par ^= 1;
+    }
+}
+
+template <int RL>
+static int persist_launch_tma(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st) {
+    using Ops = FpFwdOps2<RL>;
+    static int occ = 0, sms = 0;
+    constexpr size_t smem = 2 * 4096 * sizeof(u64);
+    auto kern = ntt_persist_tma_kernel<RL>;
+    if (occ == 0) {
+        LGPU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int o = 0;
+        LGPU_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Ops::T, smem));
+        cudaDeviceProp prop;
+        LGPU_CUDA_OK(cudaGetDeviceProperties(&prop, c->device));
+        sms = prop.multiProcessorCount;
+        occ = o > 0 ? o : 1;
+    }
+    PersistParams p;
+    p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
+    p.in_rs = in.row_stride; p.in_bs = in.batch_stride; p.out_rs = out.row_stride; p.out_bs = out.batch_stride;
+    p.logN = c->logN; p.batch = batch; p.nLT = rm.nrows * batch;
+    p.n1 = Ops::kN1; p.n2 = Ops::kN2;
+    const int per = p.n1 + p.n2;
+    const long tiles = (long)p.nLT * per;
+    int grid = sms * occ;
+    if ((long)grid > tiles) grid = (int)tiles;
+    static const int dmul = [] { const char* e = getenv("LGPU_NTT_PERSIST_D"); return e ? atoi(e) : 0; }();
+    int D = dmul > 0 ? dmul : (int)((5L * grid / 2 + per - 1) / per);
+    if (D < 1) D = 1;
+    p.D = D;
+    p.total = (p.nLT + D) * per;
+    unsigned* ctr = nullptr;
+    const size_t bytes = (size_t)(1 + p.nLT) * sizeof(unsigned);
+    LGPU_CUDA_OK(cudaMallocAsync((void**)&ctr, bytes, st));
+    LGPU_CUDA_OK(cudaMemsetAsync(ctr, 0, bytes, st));
+    p.ctr = ctr;
+    const int tma_ok = aligned16(out.p) && even_words(out.row_stride, out.batch_stride) ? 1 : 0;
+    kern<<<grid, Ops::T, smem, st>>>(p, tma_ok);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ctr, st);
+    if (e != cudaSuccess) { set_error(std::string("ntt_persist_tma_kernel: ") + cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+
 template <class Ops, bool LOOP2 = false>
 static int persist_launch(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st) {
     static int occ = 0, sms = 0;
@@ -655,9 +778,13 @@ static int persist_launch(const Ctx* c, const RowMap& rm, CSpan in, Span out, in
     return 0;
 }
 
-bool ntt_persist_supported(const Ctx* c) {
-    static const int off = [] { const char* e = getenv("LGPU_NTT_PERSIST"); return e && atoi(e) == 0 ? 1 : 0; }();
-    return !off && c->ring_type == 0 && c->logN >= 13 && c->logN <= 16;
+// LGPU_NTT_PERSIST: 0 = never, 1 = every canonical transform, unset = where it measured faster than the two-pass kernels
+// (profiles/r02_ntt_ab.json, N = 2^16 x 44 limbs x 16 polynomials): forward FP64 rows +8 %, forward integer rows +16 %;
+// the inverse transforms (256 x 16 tile code under the same loop) are 11-13 % slower than two-pass and stay there.
+bool ntt_persist_supported(const Ctx* c, bool inverse) {
+    static const int mode = [] { const char* e = getenv("LGPU_NTT_PERSIST"); return e ? atoi(e) : -1; }();
+    if (mode == 0 || c->ring_type != 0 || c->logN < 13 || c->logN > 16) return false;
+    return mode == 1 || !inverse;
 }
 
 // kind: 0 = FP64-pipe rows (all rows fp_ok), 1 / 2 = integer rows with / without lazy corrections
@@ -665,13 +792,15 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
     const int rl = c->logN - 12;
     static const int ph1int = [] { const char* e = getenv("LGPU_NTT_PH1INT"); return e ? atoi(e) : 0; }();
     // LGPU_NTT_PERSIST_V: 1 = first generation (padded tile, CTA barriers, serial ticket), 2 = first-generation tile code under
-    // the claim-ahead loop, 3 (default) = swizzled tile + pair/warp syncs + claim-ahead loop
+    // the claim-ahead loop, 3 (default) = swizzled tile + pair/warp syncs + claim-ahead loop, 4 = 3 + TMA bulk prefetch of the next chunk (measured
+    // 5 % slower than 3: profiles/r02_ntt_ab.json)
     static const int pv = [] { const char* e = getenv("LGPU_NTT_PERSIST_V"); return e ? atoi(e) : 3; }();
 #define PERSIST_CASE(RLV)                                                                                               \
     case RLV:                                                                                                           \
         if (kind == 0) {                                                                                                \
             if (inverse) return pv >= 2 ? persist_launch<FpInvOps<RLV>, true>(c, rm, in, out, batch, st) : persist_launch<FpInvOps<RLV>>(c, rm, in, out, batch, st);                               \
             if (ph1int) return persist_launch<FpFwdOps<RLV, 1>>(c, rm, in, out, batch, st);                             \
+            if (pv >= 4) return persist_launch_tma<RLV>(c, rm, in, out, batch, st);                                     \
             if (pv >= 3) return persist_launch<FpFwdOps2<RLV>, true>(c, rm, in, out, batch, st);                        \
             if (pv == 2) return persist_launch<FpFwdOps<RLV, 0>, true>(c, rm, in, out, batch, st);                      \
             return persist_launch<FpFwdOps<RLV, 0>>(c, rm, in, out, batch, st);                                         \
