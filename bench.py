@@ -320,7 +320,8 @@ def gpu_main(args):
         try:
             # ncu dram bytes of the class's launches per ciphertext pair (one --set full capture, see the file), scaled to
             # the average launch scope of this run: per_ct x pairs per step / scopes per step
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            import glob
+            tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))   # newest round's capture
             ent = tr.get(names[dom])
             if ent and ent.get("preset") == args.preset:
                 traffic = ent["dram_bytes_per_ct"] * B * args.steps / max(1, int(sc[dom]))

@@ -251,6 +251,41 @@ int lgpu_evaluator_automorphism(lgpu_ctx* ctx, int level, const uint64_t* ct_in,
 int lgpu_evaluator_relinearize(lgpu_ctx* ctx, int level, const uint64_t* ct_in, const lgpu_gadget_ct* rlk,
                                uint64_t* ct_out, int batch, void* stream);
 
+/* ---- hoisted linear transformations (circuits/common/lintrans/lintrans_evaluator.go) -------------------------------
+ * lintrans.LinearTransformation (lintrans.go:150-160) with its diagonals resident on the device. */
+typedef struct {
+    int level_q, level_p;          /* LinearTransformation.LevelQ / LevelP */
+    int log_slots;                 /* LogDimensions.Cols: rotations are taken modulo 2^log_slots */
+    int n1;                        /* N1: 0 = naive evaluator (one key per diagonal), else the BSGS baby-step count (power of two) */
+    int n_diags;                   /* len(Vec) */
+    const int* diag_index;         /* HOST: the keys of Vec */
+    const uint64_t* const* diag;   /* HOST array of DEVICE pointers; diag[i] = Vec[diag_index[i]] as a ringqp.Poly block:
+                                      (level_q+1) Q rows then (level_p+1) P rows, NTT + Montgomery form */
+} lgpu_lintrans;
+/* The GaloisKeys of an rlwe.EvaluationKeySet (core/rlwe/evaluationkeyset.go): gal_els[i] -> keys[i]. HOST arrays. */
+typedef struct {
+    int n_keys;
+    const uint64_t* gal_els;
+    const lgpu_gadget_ct* keys;
+} lgpu_galois_keys;
+/* rlwe.Parameters.GaloisElement (core/rlwe/params.go:580-583): GaloisGen^k mod NthRoot, k may be negative. */
+uint64_t lgpu_galois_element(lgpu_ctx* ctx, long long k);
+/* lintrans.Evaluator.EvaluateMany (:28-79; Evaluate / EvaluateNew are the one-matrix calls): decomposes ct_in[1] once,
+ * pre-rotates the baby steps once for all BSGS matrices (AutomorphismHoistedLazy, :82-114), then MultiplyByDiagMatrix
+ * (:141-274) or MultiplyByDiagMatrixBSGS (:280-470) per matrix. ct_in: [batch][2][level_in+1][N], NTT domain.
+ * ct_outs: HOST array of n_mats device pointers, ct_outs[i]: [batch][2][out_levels[i]+1][N]; on return out_levels[i] is the
+ * level of the result = min(out_levels[i], level_in, mats[i].level_q) (the reference Resizes opOut): rows 0..that level of
+ * each component are written, the block keeps its layout. ct_outs[i] == ct_in is allowed (EvaluateSequential, :117-139).
+ * A missing Galois key is an error ("GaloisKey[g] is missing"), like CheckAndGetGaloisKey. */
+int lgpu_lintrans_evaluate_many(lgpu_ctx* ctx, int level_in, const uint64_t* ct_in, const lgpu_lintrans* mats, int n_mats,
+                                const lgpu_galois_keys* gks, uint64_t* const* ct_outs, int* out_levels, int batch, void* stream);
+/* Evaluator.AutomorphismHoistedLazy (core/rlwe/evaluator_automorphism.go:107-165), NTT-domain ciphertexts: the result stays
+ * modulo QP, scaled by P. ct0: ctIn.Value[0] (level_q+1 rows used); decomp: lgpu_decompose_ntt output laid out for
+ * decomp_level_q >= level_q. Outputs as in lgpu_gadget_product_lazy. */
+int lgpu_evaluator_automorphism_hoisted_lazy(lgpu_ctx* ctx, int level_q, const uint64_t* ct0, const uint64_t* decomp, int decomp_level_q,
+                                             uint64_t gal_el, const lgpu_gadget_ct* gk, uint64_t* out0q, uint64_t* out0p, uint64_t* out1q,
+                                             uint64_t* out1p, int batch, size_t stride_ct, size_t stride_q, size_t stride_p, void* stream);
+
 /* ---- fused batch entry points for the measured op sequences ---------------------------------------------------
  * ckks.Evaluator.MulRelinNew(ct_a, ct_b) followed by Rescale (schemes/ckks/evaluator.go:719-872, :477-515;
  * nb_rescales = Parameters.LevelsConsumedPerRescaling(), 0 = no rescale). ct_a, ct_b: [batch][2][level+1][N]

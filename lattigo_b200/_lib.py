@@ -78,6 +78,8 @@ def lib():
             "lgpu_evaluator_relinearize": [vp, i, vp, vp, vp, i, vp],
             "lgpu_ckks_mulrelin_rescale_batch": [vp, i, vp, vp, vp, i, vp, i, vp],
             "lgpu_ckks_mulrelin_rescale_batch_host": [vp, i, vp, vp, vp, i, vp, i, i],
+            "lgpu_lintrans_evaluate_many": [vp, i, vp, vp, i, vp, vp, vp, i, vp],
+            "lgpu_evaluator_automorphism_hoisted_lazy": [vp, i, vp, vp, i, u64, vp, vp, vp, vp, vp, i, z, z, z, vp],
             "lgpu_profile_enable": [i],
             "lgpu_profile_read": [vp, vp, vp, vp],
         }
@@ -87,6 +89,8 @@ def lib():
             if name != "lgpu_destroy":
                 f.restype = i
         L.lgpu_destroy.restype = None
+        L.lgpu_galois_element.restype = c.c_uint64
+        L.lgpu_galois_element.argtypes = [vp, c.c_longlong]
         L.lgpu_launch_count.restype = c.c_ulonglong
         L.lgpu_launch_count.argtypes = []
         _lib = L
@@ -98,6 +102,17 @@ class GadgetCtStruct(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("level_q", ctypes.c_int), ("level_p", ctypes.c_int),
                 ("base_two_decomposition", ctypes.c_int), ("n_digits", ctypes.c_int), ("n_pw2_max", ctypes.c_int),
                 ("pw2_sizes", ctypes.POINTER(ctypes.c_int))]
+
+
+class LinTransStruct(ctypes.Structure):
+    """lgpu_lintrans (include/lattigo_b200.h)."""
+    _fields_ = [("level_q", ctypes.c_int), ("level_p", ctypes.c_int), ("log_slots", ctypes.c_int), ("n1", ctypes.c_int),
+                ("n_diags", ctypes.c_int), ("diag_index", ctypes.POINTER(ctypes.c_int)), ("diag", ctypes.POINTER(ctypes.c_void_p))]
+
+
+class GaloisKeysStruct(ctypes.Structure):
+    """lgpu_galois_keys (include/lattigo_b200.h)."""
+    _fields_ = [("n_keys", ctypes.c_int), ("gal_els", ctypes.POINTER(ctypes.c_uint64)), ("keys", ctypes.POINTER(GadgetCtStruct))]
 
 
 def check(rc):

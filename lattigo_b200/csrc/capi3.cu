@@ -1,0 +1,89 @@
+// capi3.cu -- extern "C" entry points of the rows that sit right above the key-switch path: hoisted linear
+// transformations (lintrans.cu).
+#include <vector>
+#include "capi_common.h"
+#include "composite.h"
+#include "lintrans.h"
+
+using namespace lgpu;
+
+static inline cudaStream_t S(void* stream) { return (cudaStream_t)stream; }
+
+static int to_gct3(const lgpu_gadget_ct* e, GadgetCt& g) {
+    REQUIRE(e && e->data, "null evaluation key");
+    REQUIRE_ALIGNED(AL(e->data));
+    g.data = (const u64*)e->data; g.levelQ = e->level_q; g.levelP = e->level_p; g.pw2 = e->base_two_decomposition;
+    g.ndigits = e->n_digits; g.npw2max = e->n_pw2_max > 0 ? e->n_pw2_max : 1; g.pw2_sizes = e->pw2_sizes;
+    return 0;
+}
+
+extern "C" {
+
+uint64_t lgpu_galois_element(lgpu_ctx* ctx, long long k) {
+    if (!ctx) return 0;
+    return galois_element(&ctx->c, k);
+}
+
+int lgpu_lintrans_evaluate_many(lgpu_ctx* ctx, int level_in, const uint64_t* ct_in, const lgpu_lintrans* mats, int n_mats,
+                                const lgpu_galois_keys* gks, uint64_t* const* ct_outs, int* out_levels, int batch, void* stream) {
+    REQUIRE_DEVICE(ctx);
+    REQUIRE(ct_in && mats && ct_outs && out_levels, "null argument");
+    REQUIRE(n_mats >= 1, "output *rlwe.Ciphertext slice is too small");
+    REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
+    REQUIRE_ALIGNED(AL(ct_in));
+    GaloisKeySet ks;
+    if (gks) {
+        REQUIRE(gks->n_keys == 0 || (gks->gal_els && gks->keys), "null Galois key arrays");
+        ks.n = gks->n_keys; ks.gal_els = (const u64*)gks->gal_els;
+        ks.keys.resize(ks.n);
+        for (int i = 0; i < ks.n; i++) {
+            if (to_gct3(&gks->keys[i], ks.keys[i])) return -1;
+            REQUIRE(ks.keys[i].pw2 == 0, "hoisted linear transformations need keys with BaseTwoDecomposition = 0");
+        }
+    }
+    std::vector<LinTransView> mv(n_mats);
+    for (int i = 0; i < n_mats; i++) {
+        const lgpu_lintrans& m = mats[i];
+        mv[i] = LinTransView{m.level_q, m.level_p, m.log_slots, m.n1, m.n_diags, m.diag_index, (const u64* const*)m.diag};
+        REQUIRE(ct_outs[i], "output slice contains unallocated ciphertext");
+        REQUIRE_ALIGNED(AL(ct_outs[i]));
+        for (int d = 0; d < m.n_diags; d++) {
+            REQUIRE(m.diag && m.diag[d], "null diagonal");
+            REQUIRE_ALIGNED(AL(m.diag[d]));
+        }
+    }
+    return lintrans_evaluate_many(&ctx->c, level_in, (const u64*)ct_in, mv.data(), n_mats, ks, (u64* const*)ct_outs, out_levels, batch, S(stream));
+}
+
+int lgpu_evaluator_automorphism_hoisted_lazy(lgpu_ctx* ctx, int level_q, const uint64_t* ct0, const uint64_t* decomp, int decomp_level_q,
+                                             uint64_t gal_el, const lgpu_gadget_ct* gk, uint64_t* out0q, uint64_t* out0p, uint64_t* out1q,
+                                             uint64_t* out1p, int batch, size_t stride_ct, size_t stride_q, size_t stride_p, void* stream) {
+    REQUIRE_DEVICE(ctx);
+    REQUIRE(ct0 && decomp && out0q && out0p && out1q && out1p, "null polynomial");
+    REQUIRE_ALIGNED(AL(ct0) && AL(decomp) && AL(out0q) && AL(out0p) && AL(out1q) && AL(out1p) && ((stride_ct | stride_q | stride_p) & 1) == 0);
+    GadgetCt g;
+    if (to_gct3(gk, g)) return -1;
+    const Ctx& c = ctx->c;
+    REQUIRE(level_q >= 0 && level_q < c.nQ && level_q <= g.levelQ, "levelQ out of range");
+    REQUIRE(g.levelP >= 0 && g.levelP < c.nP, "AutomorphismHoistedLazy requires a P ring");
+    if (decomp_level_q < 0) decomp_level_q = level_q;
+    const size_t N = c.N, nq = level_q + 1;
+    // ctIn.Value[0] * P (ringQ.MulScalarBigint, evaluator_automorphism.go:150-156)
+    std::vector<u64> pq(nq);
+    for (size_t i = 0; i < nq; i++) {
+        const u64 q = c.Q[i];
+        u64 v = 1;
+        for (int j = 0; j <= g.levelP; j++) v = h_mulmod(v, c.P[j] % q, q);
+        pq[i] = h_mform(v, q);
+    }
+    Scratch buf;
+    if (buf.alloc((size_t)batch * nq * N, S(stream))) return -1;
+    if (launch_vecop(&c, rows_range(0, 0, (int)nq), LGPU_OP_MULSCALARMONTGOMERY, CSpan{(const u64*)ct0, N, stride_ct}, CSpan{nullptr, 0, 0},
+                     Span{buf.p, N, nq * N}, batch, pq.data(), nullptr, 0, 0, c.N, S(stream))) return -1;
+    AccSpans out;
+    out.q[0] = Span{(u64*)out0q, N, stride_q}; out.q[1] = Span{(u64*)out1q, N, stride_q};
+    out.p[0] = Span{(u64*)out0p, N, stride_p}; out.p[1] = Span{(u64*)out1p, N, stride_p};
+    return automorphism_hoisted_lazy(&c, level_q, CSpan{buf.p, N, nq * N}, (const u64*)decomp, decomp_level_q, gal_el, g, out, batch, S(stream));
+}
+
+}  // extern "C"

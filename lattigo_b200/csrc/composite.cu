@@ -18,32 +18,6 @@
 
 namespace lgpu {
 
-struct Scratch {
-    u64* p = nullptr;
-    cudaStream_t st = nullptr;
-    int alloc(size_t words, cudaStream_t s) {
-        st = s;
-        LGPU_CUDA_OK(cudaMallocAsync((void**)&p, words * sizeof(u64), s));
-        return 0;
-    }
-    ~Scratch() { if (p) cudaFreeAsync(p, st); }
-};
-
-static RowMap rows_range(int limb0, int drow0, int count) {
-    RowMap rm;
-    rm.nrows = count;
-    for (int i = 0; i < count; i++) { rm.limb[i] = (unsigned char)(limb0 + i); rm.drow[i] = (unsigned char)(drow0 + i); }
-    return rm;
-}
-// QP-stacked buffer: data rows [0, nq) are Q limbs 0.., rows [nq, nq+np) are P limbs 0..
-static RowMap rows_qp(const Ctx* c, int nq, int np) {
-    RowMap rm;
-    rm.nrows = nq + np;
-    for (int i = 0; i < nq; i++) { rm.limb[i] = (unsigned char)i; rm.drow[i] = (unsigned char)i; }
-    for (int j = 0; j < np; j++) { rm.limb[nq + j] = (unsigned char)(c->nQ + j); rm.drow[nq + j] = (unsigned char)(nq + j); }
-    return rm;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // ModDown
 // ---------------------------------------------------------------------------------------------------------
@@ -323,7 +297,8 @@ struct MacParams {
     const LimbConst* limbs;
     const u64* evk0; const u64* evk1;      // row r of the key = evk + erow(r) * N
     int nQk;                               // Q rows in the key
-    const u64* xa; size_t xa_rs, xa_bs;    // decomposition buffer, QP stacked with nq Q rows
+    const u64* xa; size_t xa_rs, xa_bs;    // decomposition buffer, QP stacked with nq + xa_pshift Q rows
+    int xa_pshift;                         // the buffer was laid out for a higher level: its P rows start xa_pshift rows later
     const u64* xb; size_t xb_rs, xb_bs;    // NTT input (digit rows)
     int dlo, dhi;
     u64* accQ[2]; size_t accQ_rs, accQ_bs;
@@ -344,7 +319,8 @@ __global__ void __launch_bounds__(256) mac_kernel(MacParams p) {
     const ulonglong2 e1 = reinterpret_cast<const ulonglong2*>(p.evk1 + erow * p.n)[i];
     const bool fromB = (!isP) && r >= p.dlo && r < p.dhi;
     for (int b = blockIdx.z; b < p.batch; b += gridDim.z) {
-        const u64* xrow = fromB ? p.xb + (size_t)b * p.xb_bs + (size_t)r * p.xb_rs : p.xa + (size_t)b * p.xa_bs + (size_t)r * p.xa_rs;
+        const u64* xrow = fromB ? p.xb + (size_t)b * p.xb_bs + (size_t)r * p.xb_rs
+                                : p.xa + (size_t)b * p.xa_bs + (size_t)(isP ? r + p.xa_pshift : r) * p.xa_rs;
         const ulonglong2 x = reinterpret_cast<const ulonglong2*>(xrow)[i];
         u64* a0 = isP ? p.accP[0] + (size_t)b * p.accP_bs + (size_t)j * p.accP_rs : p.accQ[0] + (size_t)b * p.accQ_bs + (size_t)j * p.accQ_rs;
         u64* a1 = isP ? p.accP[1] + (size_t)b * p.accP_bs + (size_t)j * p.accP_rs : p.accQ[1] + (size_t)b * p.accQ_bs + (size_t)j * p.accQ_rs;
@@ -569,8 +545,12 @@ int decompose_ntt(const Ctx* c, int levelQ, int levelP, int nbPi, CSpan c2, bool
 }
 
 // gadgetProductMultiplePLazyHoisted (:401-453): pure MAC over the pre-decomposed digits.
-int gadget_product_hoisted_lazy(const Ctx* c, int levelQ, const u64* decomp, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st) {
+int gadget_product_hoisted_lazy(const Ctx* c, int levelQ, const u64* decomp, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st,
+                                int decomp_levelQ) {
     if (check_evk(c, levelQ, evk)) return -1;
+    if (decomp_levelQ < 0) decomp_levelQ = levelQ;
+    if (decomp_levelQ < levelQ) { set_error("the decomposition was computed at a lower level than levelQ"); return -1; }
+    const size_t nqd = decomp_levelQ + 1;
     if (evk.pw2 != 0) { set_error("method is unsupported for BaseTwoDecomposition != 0"); return -1; }
     if (evk.levelP < 0) { set_error("hoisted gadget product requires a P ring"); return -1; }
     const int levelP = evk.levelP;
@@ -580,7 +560,7 @@ int gadget_product_hoisted_lazy(const Ctx* c, int levelQ, const u64* decomp, con
         MacParams m;
         memset(&m, 0, sizeof(m));
         m.limbs = c->d_limbs; m.evk0 = evk.at(i, 0, 0, N); m.evk1 = evk.at(i, 0, 1, N); m.nQk = evk.levelQ + 1;
-        m.xa = decomp + (size_t)i * batch * (nq + np) * N; m.xa_rs = N; m.xa_bs = (nq + np) * N;
+        m.xa = decomp + (size_t)i * batch * (nqd + np) * N; m.xa_rs = N; m.xa_bs = (nqd + np) * N; m.xa_pshift = (int)(nqd - nq);
         m.xb = nullptr; m.dlo = m.dhi = 0;
         for (int k = 0; k < 2; k++) { m.accQ[k] = acc.q[k].p; m.accP[k] = acc.p[k].p; }
         m.accQ_rs = acc.q[0].row_stride; m.accQ_bs = acc.q[0].batch_stride; m.accP_rs = acc.p[0].row_stride; m.accP_bs = acc.p[0].batch_stride;

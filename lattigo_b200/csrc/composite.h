@@ -20,6 +20,32 @@ struct AccSpans {  // the four accumulator polynomials of a ctQP: [comp].Q (leve
     Span p[2];
 };
 
+struct Scratch {
+    u64* p = nullptr;
+    cudaStream_t st = nullptr;
+    int alloc(size_t words, cudaStream_t s) {
+        st = s;
+        LGPU_CUDA_OK(cudaMallocAsync((void**)&p, words * sizeof(u64), s));
+        return 0;
+    }
+    ~Scratch() { if (p) cudaFreeAsync(p, st); }
+};
+
+inline RowMap rows_range(int limb0, int drow0, int count) {
+    RowMap rm;
+    rm.nrows = count;
+    for (int i = 0; i < count; i++) { rm.limb[i] = (unsigned char)(limb0 + i); rm.drow[i] = (unsigned char)(drow0 + i); }
+    return rm;
+}
+// QP-stacked buffer: data rows [0, nq) are Q limbs 0.., rows [nq, nq+np) are P limbs 0..
+inline RowMap rows_qp(const Ctx* c, int nq, int np) {
+    RowMap rm;
+    rm.nrows = nq + np;
+    for (int i = 0; i < nq; i++) { rm.limb[i] = (unsigned char)i; rm.drow[i] = (unsigned char)i; }
+    for (int j = 0; j < np; j++) { rm.limb[nq + j] = (unsigned char)(c->nQ + j); rm.drow[nq + j] = (unsigned char)(nq + j); }
+    return rm;
+}
+
 int base_rns_decomposition_vector_size(int levelQ, int levelP);
 int moddown_qp_to_q(const Ctx* c, int levelQ, int levelP, CSpan p1Q, CSpan p1P, Span p2Q, int batch, cudaStream_t st);
 int moddown_qp_to_q_ntt(const Ctx* c, int levelQ, int levelP, CSpan p1Q, CSpan p1P, Span p2Q, int batch, cudaStream_t st);
@@ -36,7 +62,9 @@ int decompose_ntt(const Ctx* c, int levelQ, int levelP, int nbPi, CSpan c2, bool
 int gadget_product_lazy(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st);
 int evaluator_moddown_ntt(const Ctx* c, int levelQ, int levelP, const AccSpans& acc, Span ct0, Span ct1, int batch, cudaStream_t st);
 int gadget_product(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, Span ct0, Span ct1, int batch, cudaStream_t st);
-int gadget_product_hoisted_lazy(const Ctx* c, int levelQ, const u64* decomp, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st);
+// decomp_levelQ: level the DecomposeNTT buffer was laid out for (>= levelQ; -1 = levelQ) -- lintrans uses one decomposition for matrices of lower levels
+int gadget_product_hoisted_lazy(const Ctx* c, int levelQ, const u64* decomp, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st,
+                                int decomp_levelQ = -1);
 int gadget_product_hoisted(const Ctx* c, int levelQ, const u64* decomp, const GadgetCt& evk, Span ct0, Span ct1, int batch, cudaStream_t st);
 int evaluator_automorphism(const Ctx* c, int level, CSpan in0, CSpan in1, u64 galEl, const GadgetCt& gk, Span out0, Span out1,
                            const u64* decomp_hoisted, int batch, cudaStream_t st);
