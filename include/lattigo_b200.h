@@ -286,6 +286,29 @@ int lgpu_evaluator_automorphism_hoisted_lazy(lgpu_ctx* ctx, int level_q, const u
                                              uint64_t gal_el, const lgpu_gadget_ct* gk, uint64_t* out0q, uint64_t* out0p, uint64_t* out1q,
                                              uint64_t* out1p, int batch, size_t stride_ct, size_t stride_q, size_t stride_p, void* stream);
 
+/* ---- wire format -> device (the reference's WriteTo / ReadFrom byte streams, little-endian uint64 words) ------------------
+ * ring.Poly (ring/poly.go:132-179): rows, then per row {len, len words}. */
+int lgpu_poly_load(lgpu_ctx* ctx, const void* bytes, size_t nbytes, uint64_t* dst, int rows_cap, int* rows_out, size_t* consumed,
+                   void* stream);
+/* ring.Poly.WriteTo of `rows` device rows into `bytes` (8 + rows * (8 + 8 N) bytes); synchronises `stream`. */
+int lgpu_poly_store(lgpu_ctx* ctx, const uint64_t* src, int rows, void* bytes, size_t cap, size_t* written, void* stream);
+#define LGPU_MAX_DIGITS 128
+typedef struct {
+    int level_q, level_p, base_two_decomposition, n_digits, n_pw2_max;
+    int pw2_sizes[LGPU_MAX_DIGITS];   /* len(Value[i]); usable as lgpu_gadget_ct.pw2_sizes */
+    size_t device_bytes;              /* size of the device block in the lgpu_gadget_ct layout */
+    size_t consumed;                  /* bytes of the stream that belong to this object */
+} lgpu_evk_info;
+/* rlwe.GadgetCiphertext.ReadFrom / UnmarshalBinary (core/rlwe/gadgetciphertext.go:101-167; also EvaluationKey and
+ * RelinearizationKey, which are GadgetCiphertexts): BaseTwoDecomposition, then structs.Matrix[VectorQP]
+ * (utils/structs/matrix.go:80-140). With dst == NULL only *info is filled (no device work); with a 16-byte aligned device
+ * block of info->device_bytes bytes the rows are copied straight from the byte stream into the lgpu_gadget_ct layout. */
+int lgpu_gadget_ct_load(lgpu_ctx* ctx, const void* bytes, size_t nbytes, uint64_t* dst, size_t dst_bytes, lgpu_evk_info* info,
+                        void* stream);
+/* rlwe.GaloisKey.ReadFrom (core/rlwe/keys.go:628-700): GaloisElement, NthRoot, EvaluationKey. */
+int lgpu_galois_key_load(lgpu_ctx* ctx, const void* bytes, size_t nbytes, uint64_t* gal_el, uint64_t* nth_root, uint64_t* dst,
+                         size_t dst_bytes, lgpu_evk_info* info, void* stream);
+
 /* ---- fused batch entry points for the measured op sequences ---------------------------------------------------
  * ckks.Evaluator.MulRelinNew(ct_a, ct_b) followed by Rescale (schemes/ckks/evaluator.go:719-872, :477-515;
  * nb_rescales = Parameters.LevelsConsumedPerRescaling(), 0 = no rescale). ct_a, ct_b: [batch][2][level+1][N]

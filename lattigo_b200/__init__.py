@@ -8,3 +8,4 @@ from .rlwe import (GadgetCiphertext, BasisExtender, Decomposer, Evaluator, CKKSE
                    automorphism_ntt_index, automorphism_ntt_with_index, automorphism_ntt, automorphism)
 from .ringqp import RingQP, Poly as PolyQP  # noqa: F401
 from . import lintrans  # noqa: F401,E402
+from . import wire  # noqa: F401,E402

@@ -80,6 +80,10 @@ def lib():
             "lgpu_ckks_mulrelin_rescale_batch_host": [vp, i, vp, vp, vp, i, vp, i, i],
             "lgpu_lintrans_evaluate_many": [vp, i, vp, vp, i, vp, vp, vp, i, vp],
             "lgpu_evaluator_automorphism_hoisted_lazy": [vp, i, vp, vp, i, u64, vp, vp, vp, vp, vp, i, z, z, z, vp],
+            "lgpu_poly_load": [vp, vp, z, vp, i, vp, vp, vp],
+            "lgpu_poly_store": [vp, vp, i, vp, z, vp, vp],
+            "lgpu_gadget_ct_load": [vp, vp, z, vp, z, vp, vp],
+            "lgpu_galois_key_load": [vp, vp, z, vp, vp, vp, z, vp, vp],
             "lgpu_profile_enable": [i],
             "lgpu_profile_read": [vp, vp, vp, vp],
         }
@@ -102,6 +106,12 @@ class GadgetCtStruct(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("level_q", ctypes.c_int), ("level_p", ctypes.c_int),
                 ("base_two_decomposition", ctypes.c_int), ("n_digits", ctypes.c_int), ("n_pw2_max", ctypes.c_int),
                 ("pw2_sizes", ctypes.POINTER(ctypes.c_int))]
+
+
+class EvkInfoStruct(ctypes.Structure):
+    """lgpu_evk_info (include/lattigo_b200.h)."""
+    _fields_ = [("level_q", ctypes.c_int), ("level_p", ctypes.c_int), ("base_two_decomposition", ctypes.c_int), ("n_digits", ctypes.c_int),
+                ("n_pw2_max", ctypes.c_int), ("pw2_sizes", ctypes.c_int * 128), ("device_bytes", ctypes.c_size_t), ("consumed", ctypes.c_size_t)]
 
 
 class LinTransStruct(ctypes.Structure):

@@ -248,9 +248,8 @@ int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64
     // Two independent streams, each doing H2D -> compute -> D2H for alternating chunks: the copies of one chunk overlap
     // the compute of the other (copy engines run concurrently with the SMs). Streams and staging buffers live in the
     // context; one host-pipeline call at a time per context.
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
     Ctx::HostPipe& hp = ctx->c.host_pipe;
+    std::lock_guard<std::mutex> lock(hp.mu);
     int rc = 0;
     const size_t need[3] = {chunk * in_words, chunk * in_words, chunk * out_words};
     for (int i = 0; i < 2 && !rc; i++) {

@@ -462,6 +462,13 @@ static int check_evk(const Ctx* c, int levelQ, const GadgetCt& evk) {
     if (!evk.data) { set_error("null evaluation key"); return -1; }
     if (evk.levelQ < 0 || evk.levelQ >= c->nQ || evk.levelP < -1 || evk.levelP >= c->nP) { set_error("evaluation key levels out of range"); return -1; }
     if (levelQ < 0 || levelQ > evk.levelQ) { set_error("levelQ out of range for this evaluation key"); return -1; }
+    // shape of Value[digit][pw2] against what the products will index (core/rlwe/params.go:543-565)
+    const int nd = evk.levelP > 0 ? base_rns_decomposition_vector_size(levelQ, evk.levelP) : levelQ + 1;
+    if (evk.ndigits < nd) { set_error("evaluation key has fewer digits than BaseRNSDecompositionVectorSize(levelQ, levelP)"); return -1; }
+    if (evk.npw2max < 1) { set_error("evaluation key: n_pw2_max must be >= 1"); return -1; }
+    if (evk.pw2_sizes)
+        for (int i = 0; i < nd; i++)
+            if (evk.pw2_sizes[i] < 1 || evk.pw2_sizes[i] > evk.npw2max) { set_error("evaluation key: pw2_sizes[i] out of [1, n_pw2_max]"); return -1; }
     return 0;
 }
 

@@ -10,6 +10,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -105,6 +106,7 @@ struct Ctx {
         cudaStream_t st[2] = {nullptr, nullptr};
         u64* buf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [stream][A, B, out]
         size_t cap[3] = {0, 0, 0};                                                       // words per buffer kind
+        std::mutex mu;                                                                   // one host-pipeline call at a time PER CONTEXT (contexts on other GPUs run concurrently)
     } host_pipe;
 };
 

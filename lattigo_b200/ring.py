@@ -184,8 +184,19 @@ class Ring:
         assert t.shape[0] >= self.level + 1
         return 1, 0
 
+    def _same_layout(self, ref, *others):
+        """The C ABI applies ONE (batch, batch stride) to every operand of a call: batched operands of another limb count
+        (polynomials of different levels under AtLevel) would be read with the wrong stride."""
+        for t in others:
+            if t is not None and t.dim() == 3 and ref.dim() == 3:
+                assert t.shape[0] == ref.shape[0] and t.shape[1] == ref.shape[1], \
+                    "batched operands must share the batch size and the limb count of the output (one batch stride per call)"
+            elif t is not None:
+                assert t.dim() == ref.dim(), "operands must be all batched or all single polynomials"
+
     def _ntt(self, inverse, p1, p2, lazy):
         b, bs = self._batch(p2)
+        self._same_layout(p2, p1)
         f = _lib.lib().lgpu_intt if inverse else _lib.lib().lgpu_ntt
         _lib.check(f(self.ctx.h, self.which, self.level, _dptr(p1), _dptr(p2), lazy, b, bs, _stream()))
 
@@ -196,6 +207,7 @@ class Ring:
 
     def _vec(self, name, p1, p2, p3, s0=None, s1=None):
         b, bs = self._batch(p3)
+        self._same_layout(p3, p1, p2)
         a0, p0 = _u64arr(s0)
         a1, pp1 = _u64arr(s1)
         _lib.check(_lib.lib().lgpu_vecop(self.ctx.h, self.which, self.level, OP[name], _dptr(p1), _dptr(p2), _dptr(p3),

@@ -118,3 +118,37 @@ def keyswitch_noise_log2(params: O.Parameters, levelQ, cx_ntt, ct, s_in, s_out):
     vals = ringQ.PolyToBigint(back)
     m = max(min(v, Q - v) for v in vals)
     return float(np.log2(float(m))) if m else 0.0
+
+
+# ---- the reference's wire format, written the way its WriteTo methods do (little-endian uint64 words) --------------------
+def marshal_poly(rows) -> bytes:
+    """ring.Poly.MarshalBinary (ring/poly.go:132-142 -> structs.Matrix[uint64].WriteTo, utils/structs/matrix.go:80-108)."""
+    rows = np.asarray(rows, dtype=U64)
+    out = [np.array([rows.shape[0]], dtype="<u8").tobytes()]
+    for r in rows:
+        out.append(np.array([r.shape[0]], dtype="<u8").tobytes())
+        out.append(np.ascontiguousarray(r).astype("<u8").tobytes())
+    return b"".join(out)
+
+
+def marshal_gadget_ct(gct: "O.GadgetCiphertext") -> bytes:
+    """rlwe.GadgetCiphertext.MarshalBinary (core/rlwe/gadgetciphertext.go:101-121): BaseTwoDecomposition, then
+    structs.Matrix[VectorQP]: len(Value), per digit len(Value[i]), per entry len(VectorQP) = 2, per ringqp.Poly Q then P."""
+    d = gct.data
+    nq = gct.nQ
+    n_digits = d.shape[0]
+    sizes = list(gct.pw2_sizes)
+    out = [np.array([gct.BaseTwoDecomposition, n_digits], dtype="<u8").tobytes()]
+    for i in range(n_digits):
+        out.append(np.array([sizes[i]], dtype="<u8").tobytes())
+        for j in range(sizes[i]):
+            out.append(np.array([2], dtype="<u8").tobytes())
+            for k in range(2):
+                out.append(marshal_poly(d[i, j, k, :nq]))
+                out.append(marshal_poly(d[i, j, k, nq:]))
+    return b"".join(out)
+
+
+def marshal_galois_key(gal_el: int, nth_root: int, gct) -> bytes:
+    """rlwe.GaloisKey.MarshalBinary (core/rlwe/keys.go:628-657)."""
+    return np.array([gal_el, nth_root], dtype="<u8").tobytes() + marshal_gadget_ct(gct)
