@@ -127,6 +127,11 @@ int lgpu_ntt(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t* o
              int batch, size_t batch_stride, void* stream);
 int lgpu_intt(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t* out, int lazy,
               int batch, size_t batch_stride, void* stream);
+/* Ring.NTT(in, out) followed by Ring.MulCoeffsMontgomery(out, other, out) (ring/ntt.go:127-131 + ring/operations.go:88-92) as
+ * one pass over HBM: the product is applied in the transform's last pass (N = 2^13..2^16; two launches otherwise).
+ * `other` must not alias `out`; in == out is allowed. */
+int lgpu_ntt_then_mul_coeffs_montgomery(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, const uint64_t* other,
+                                        uint64_t* out, int batch, size_t batch_stride, void* stream);
 /* SubRing.NTT / NTTLazy / INTT / INTTLazy on one row (ring/subring_ops.go:235-253) */
 int lgpu_subring_ntt(lgpu_ctx* ctx, int ring, int limb, const uint64_t* in, uint64_t* out, int lazy, void* stream);
 int lgpu_subring_intt(lgpu_ctx* ctx, int ring, int limb, const uint64_t* in, uint64_t* out, int lazy, void* stream);

@@ -48,6 +48,7 @@ def lib():
             "lgpu_memcpy_d2h": [vp, vp, vp, z, vp],
             "lgpu_ntt": [vp, i, i, vp, vp, i, i, z, vp],
             "lgpu_intt": [vp, i, i, vp, vp, i, i, z, vp],
+            "lgpu_ntt_then_mul_coeffs_montgomery": [vp, i, i, vp, vp, vp, i, z, vp],
             "lgpu_subring_ntt": [vp, i, i, vp, vp, i, vp],
             "lgpu_subring_intt": [vp, i, i, vp, vp, i, vp],
             "lgpu_vecop": [vp, i, i, i, vp, vp, vp, vp, vp, i, z, vp],

@@ -163,6 +163,16 @@ int lgpu_ntt(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t* o
     if (make_rowmap(ctx->c, ring, level, rm)) return -1;
     return ntt_common(ctx, false, rm, in, out, lazy, batch, batch_stride, stream);
 }
+int lgpu_ntt_then_mul_coeffs_montgomery(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, const uint64_t* other, uint64_t* out, int batch,
+                                        size_t batch_stride, void* stream) {
+    REQUIRE_DEVICE(ctx);
+    REQUIRE(in && other && out, "null polynomial");
+    RowMap rm;
+    if (make_rowmap(ctx->c, ring, level, rm)) return -1;
+    const size_t N = ctx->c.N;
+    return launch_ntt_mul_montgomery(&ctx->c, rm, CSpan{(const u64*)in, N, batch_stride}, CSpan{(const u64*)other, N, batch_stride},
+                                     Span{(u64*)out, N, batch_stride}, batch, (cudaStream_t)stream);
+}
 int lgpu_intt(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, uint64_t* out, int lazy, int batch, size_t batch_stride, void* stream) {
     REQUIRE_DEVICE(ctx);
     RowMap rm;

@@ -170,7 +170,11 @@ int launch_ntt_fp64(const Ctx* c, const RowMap& rm, bool inverse, CSpan in, Span
 
 // ntt_persist.cu: single-launch, single-HBM-pass transforms (2^13 <= N <= 2^16); kind 0 = FP64-pipe rows, 1 / 2 = integer rows
 bool ntt_persist_supported(const Ctx* c, bool inverse);
-int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, CSpan in, Span out, int batch, cudaStream_t st);
+int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, CSpan in, Span out, int batch, cudaStream_t st,
+                       CSpan mul = CSpan{nullptr, 0, 0});
+// Ring.NTT followed by Ring.MulCoeffsMontgomery(., other, out) (ring/ntt.go:127-131 + ring/operations.go:88-92): fused into the
+// transform's last pass where the persistent kernels apply, two launches otherwise (ntt.cu)
+int launch_ntt_mul_montgomery(const Ctx* c, const RowMap& rm, CSpan in, CSpan other, Span out, int batch, cudaStream_t st);
 
 // basisext.cu
 int launch_modup_qp(const Ctx* c, bool toP, int levelQ, int levelP, CSpan in, Span out, int batch, cudaStream_t st);

@@ -326,6 +326,36 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     return launch_ntt_int(c, rm, in, out, batch, mode, st);
 }
 
+// Ring.NTT + Ring.MulCoeffsMontgomery in one pass: algorithmic traffic 3 rows (in, other, out) instead of the
+// 5 of the two-call sequence.
+int launch_ntt_mul_montgomery(const Ctx* c, const RowMap& rm, CSpan in, CSpan other, Span out, int batch, cudaStream_t st) {
+    if (check_common(c, rm, batch)) return -1;
+    if (!other.p) { set_error("null operand"); return -1; }
+    if (other.p == out.p) { set_error("NTT+MulCoeffsMontgomery: the multiplicand cannot be the output"); return -1; }
+    if (c->ring_type == 0 && ntt_persist_supported(c, false)) {
+        RowMap fp, rest;
+        if (!split_rows_fp64(c, rm, fp, rest)) { rest = rm; fp.nrows = 0; }
+        if (fp.nrows > 0) {
+            ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 24.0 * c->N * fp.nrows * batch, 1);
+            if (launch_ntt_persist(c, fp, false, 0, in, out, batch, st, other)) return -1;
+        }
+        // integer rows: group by correction kind like launch_ntt_int does (fast_variant is per launch)
+        if (rest.nrows > 0) {
+            const int fast = fast_variant(c, rest, false);
+            if (fast != 0) {
+                ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 24.0 * c->N * rest.nrows * batch, 1);
+                return launch_ntt_persist(c, rest, false, fast, in, out, batch, st, other);
+            }
+            if (launch_ntt_int(c, rest, in, out, batch, NTT_CANONICAL, st)) return -1;
+            return launch_vecop(c, rest, LGPU_OP_MULCOEFFSMONTGOMERY, CSpan{out.p, out.row_stride, out.batch_stride}, other, out, batch, nullptr, nullptr, 0, 0,
+                                c->N, st);
+        }
+        return 0;
+    }
+    if (launch_ntt(c, rm, in, out, batch, NTT_CANONICAL, st)) return -1;
+    return launch_vecop(c, rm, LGPU_OP_MULCOEFFSMONTGOMERY, CSpan{out.p, out.row_stride, out.batch_stride}, other, out, batch, nullptr, nullptr, 0, 0, c->N, st);
+}
+
 int launch_intt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, int mode, cudaStream_t st) {
     if (check_common(c, rm, batch)) return -1;
     if (c->ring_type != 0) return launch_ntt_ci(c, rm, true, in, out, batch, mode == NTT_EXACT_LAZY, st);

@@ -43,6 +43,10 @@ struct PersistParams {
     int D;                  // distance (in limb-transforms) between the pass-1 and the pass-2 tiles of one step
     int total;              // tickets = (nLT + D) * (n1 + n2)
     unsigned* ctr;          // [0]: ticket dispenser; [1 + lt]: finished pass-1 tiles of lt
+    // optional fused epilogue (forward transforms): out = MulCoeffsMontgomery(NTT(in), mul) -- ring/ntt.go:127-131 followed by
+    // ring/operations.go:88-92 in one pass (3 rows of traffic instead of 5); the product runs on the integer
+    // pipes, which the FP64-pipe transform leaves idle
+    const u64* mul; size_t mul_rs, mul_bs;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -54,6 +58,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 struct TileRef {
     const u64* in;
     u64* out;
+    const u64* mul;
     int limb;
 };
 __device__ __forceinline__ TileRef tile_ref(const PersistParams& p, int lt) {
@@ -62,6 +67,7 @@ __device__ __forceinline__ TileRef tile_ref(const PersistParams& p, int lt) {
     TileRef t;
     t.in = p.in + (size_t)b * p.in_bs + (size_t)row * p.in_rs;
     t.out = p.out + (size_t)b * p.out_bs + (size_t)row * p.out_rs;
+    t.mul = p.mul ? p.mul + (size_t)b * p.mul_bs + (size_t)row * p.mul_rs : nullptr;
     t.limb = p.rm.limb[r];
     return t;
 }
@@ -186,8 +192,15 @@ struct FpFwdOps {
             for (int k = 0; k < 8; k++) smem[fpad(base + k)] = bred_add(fp_biased_u64(x[k], off52), q, bhi);
         }
         __syncthreads();
+        if (t.mul) {
+            const u64* mu = t.mul + ((size_t)chunk << 12);
+            const u64 q = L.q, qinv = L.qinv;
 #pragma unroll
-        for (int k = 0; k < 8; k++) io[k * T + tid] = smem[fpad(k * T + tid)];
+            for (int k = 0; k < 8; k++) io[k * T + tid] = mred(smem[fpad(k * T + tid)], mu[k * T + tid], q, qinv);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) io[k * T + tid] = smem[fpad(k * T + tid)];
+        }
     }
 };
 
@@ -276,11 +289,12 @@ struct FpFwdOps2 : FpFwdOps<RL, 0> {
         u64* io = t.out + ((size_t)chunk << 12);
         round1<0>(L, io, smem, chunk, threadIdx.x);
         __syncthreads();
-        tail(p, L, io, smem, chunk, threadIdx.x);
+        tail(p, L, io, smem, chunk, threadIdx.x, t.mul);
     }
 
     // rounds 2..4 and the copy-out; the caller has issued the CTA barrier that follows round 1
-    static __device__ __forceinline__ void tail(const PersistParams& p, const LimbConst& L, u64* io, u64* smem, int chunk, int tid) {
+    static __device__ __forceinline__ void tail(const PersistParams& p, const LimbConst& L, u64* io, u64* smem, int chunk, int tid,
+                                                const u64* mul = nullptr) {
         constexpr int s1 = RL;
         double* fsm = reinterpret_cast<double*>(smem);
         const double fq = L.fq, fqinv = L.fqinv;
@@ -310,8 +324,18 @@ struct FpFwdOps2 : FpFwdOps<RL, 0> {
             const int w0 = (tid >> 5) << 8, lane = tid & 31;
             const int tb = swz(w0 + lane);
             u64* g = io + w0 + lane;
+            if (mul) {
+                const u64* mu = mul + ((size_t)chunk << 12) + w0 + lane;
+                const u64 q = L.q, qinv = L.qinv;
+                u64 o[8];
 #pragma unroll
-            for (int m = 0; m < 8; m++) g[32 * m] = smem[(tb ^ ((m & 1) << 2) ^ (((m >> 1) & 1) * 9)) + 32 * m];
+                for (int m = 0; m < 8; m++) o[m] = __ldg(mu + 32 * m);
+#pragma unroll
+                for (int m = 0; m < 8; m++) g[32 * m] = mred(smem[(tb ^ ((m & 1) << 2) ^ (((m >> 1) & 1) * 9)) + 32 * m], o[m], q, qinv);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; m++) g[32 * m] = smem[(tb ^ ((m & 1) << 2) ^ (((m >> 1) & 1) * 9)) + 32 * m];
+            }
         }
     }
 };
@@ -435,7 +459,8 @@ struct IntFwdOps {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const int idx = k * T + tid;
-            io[idx] = bred_add(sm[pad_idx(idx)], q, bhi);                         // reducevec, ring/ntt.go:176
+            const u64 v = bred_add(sm[pad_idx(idx)], q, bhi);                     // reducevec, ring/ntt.go:176
+            io[idx] = t.mul ? mred(v, t.mul[((size_t)chunk << CL) + idx], q, L.qinv) : v;
         }
     }
 };
@@ -682,7 +707,7 @@ __global__ void __launch_bounds__(512, 2) ntt_persist_tma_kernel(PersistParams p
                 if (tid == 0) publish();
                 done_publish = true;
                 __syncthreads();
-                Ops::tail(p, L, io, buf, chunk, tid);
+                Ops::tail(p, L, io, buf, chunk, tid, tr.mul);
             }
         }
         if (!done_publish && tid == 0) publish();
@@ -696,7 +721,7 @@ __global__ void __launch_bounds__(512, 2) ntt_persist_tma_kernel(PersistParams p
 }
 
 template <int RL>
-static int persist_launch_tma(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st) {
+static int persist_launch_tma(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st, CSpan mul) {
     using Ops = FpFwdOps2<RL>;
     static int occ = 0, sms = 0;
     constexpr size_t smem = 2 * 4096 * sizeof(u64);
@@ -714,6 +739,7 @@ static int persist_launch_tma(const Ctx* c, const RowMap& rm, CSpan in, Span out
     p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
     p.in_rs = in.row_stride; p.in_bs = in.batch_stride; p.out_rs = out.row_stride; p.out_bs = out.batch_stride;
     p.logN = c->logN; p.batch = batch; p.nLT = rm.nrows * batch;
+    p.mul = mul.p; p.mul_rs = mul.row_stride; p.mul_bs = mul.batch_stride;
     p.n1 = Ops::kN1; p.n2 = Ops::kN2;
     const int per = p.n1 + p.n2;
     const long tiles = (long)p.nLT * per;
@@ -738,7 +764,7 @@ static int persist_launch_tma(const Ctx* c, const RowMap& rm, CSpan in, Span out
 }
 
 template <class Ops, bool LOOP2 = false>
-static int persist_launch(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st) {
+static int persist_launch(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st, CSpan mul) {
     static int occ = 0, sms = 0;
     auto kern = LOOP2 ? ntt_persist2_kernel<Ops> : ntt_persist_kernel<Ops>;
     if (occ == 0) {
@@ -754,6 +780,7 @@ static int persist_launch(const Ctx* c, const RowMap& rm, CSpan in, Span out, in
     p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
     p.in_rs = in.row_stride; p.in_bs = in.batch_stride; p.out_rs = out.row_stride; p.out_bs = out.batch_stride;
     p.logN = c->logN; p.batch = batch; p.nLT = rm.nrows * batch;
+    p.mul = mul.p; p.mul_rs = mul.row_stride; p.mul_bs = mul.batch_stride;
     p.n1 = Ops::kN1; p.n2 = Ops::kN2;
     const int per = p.n1 + p.n2;
     const long tiles = (long)p.nLT * per;
@@ -788,7 +815,8 @@ bool ntt_persist_supported(const Ctx* c, bool inverse) {
 }
 
 // kind: 0 = FP64-pipe rows (all rows fp_ok), 1 / 2 = integer rows with / without lazy corrections
-int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, CSpan in, Span out, int batch, cudaStream_t st) {
+int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, CSpan in, Span out, int batch, cudaStream_t st, CSpan mul) {
+    if (mul.p && inverse) { set_error("the fused multiply epilogue exists for forward transforms only"); return -1; }
     const int rl = c->logN - 12;
     static const int ph1int = [] { const char* e = getenv("LGPU_NTT_PH1INT"); return e ? atoi(e) : 0; }();
     // LGPU_NTT_PERSIST_V: 1 = first generation (padded tile, CTA barriers, serial ticket), 2 = first-generation tile code under
@@ -798,23 +826,23 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
 #define PERSIST_CASE(RLV)                                                                                               \
     case RLV:                                                                                                           \
         if (kind == 0) {                                                                                                \
-            if (inverse) return pv >= 2 ? persist_launch<FpInvOps<RLV>, true>(c, rm, in, out, batch, st) : persist_launch<FpInvOps<RLV>>(c, rm, in, out, batch, st);                               \
-            if (ph1int) return persist_launch<FpFwdOps<RLV, 1>>(c, rm, in, out, batch, st);                             \
-            if (pv >= 4) return persist_launch_tma<RLV>(c, rm, in, out, batch, st);                                     \
-            if (pv >= 3) return persist_launch<FpFwdOps2<RLV>, true>(c, rm, in, out, batch, st);                        \
-            if (pv == 2) return persist_launch<FpFwdOps<RLV, 0>, true>(c, rm, in, out, batch, st);                      \
-            return persist_launch<FpFwdOps<RLV, 0>>(c, rm, in, out, batch, st);                                         \
+            if (inverse) return pv >= 2 ? persist_launch<FpInvOps<RLV>, true>(c, rm, in, out, batch, st, mul) : persist_launch<FpInvOps<RLV>>(c, rm, in, out, batch, st, mul);                               \
+            if (ph1int) return persist_launch<FpFwdOps<RLV, 1>>(c, rm, in, out, batch, st, mul);                             \
+            if (pv >= 4) return persist_launch_tma<RLV>(c, rm, in, out, batch, st, mul);                                     \
+            if (pv >= 3) return persist_launch<FpFwdOps2<RLV>, true>(c, rm, in, out, batch, st, mul);                        \
+            if (pv == 2) return persist_launch<FpFwdOps<RLV, 0>, true>(c, rm, in, out, batch, st, mul);                      \
+            return persist_launch<FpFwdOps<RLV, 0>>(c, rm, in, out, batch, st, mul);                                         \
         }                                                                                                               \
         if (pv >= 2) {                                                                                                  \
-            if (kind == 1) return inverse ? persist_launch<IntInvOps<RLV, 1>, true>(c, rm, in, out, batch, st)          \
-                                          : persist_launch<IntFwdOps<RLV, 1>, true>(c, rm, in, out, batch, st);         \
-            return inverse ? persist_launch<IntInvOps<RLV, 2>, true>(c, rm, in, out, batch, st)                         \
-                           : persist_launch<IntFwdOps<RLV, 2>, true>(c, rm, in, out, batch, st);                        \
+            if (kind == 1) return inverse ? persist_launch<IntInvOps<RLV, 1>, true>(c, rm, in, out, batch, st, mul)          \
+                                          : persist_launch<IntFwdOps<RLV, 1>, true>(c, rm, in, out, batch, st, mul);         \
+            return inverse ? persist_launch<IntInvOps<RLV, 2>, true>(c, rm, in, out, batch, st, mul)                         \
+                           : persist_launch<IntFwdOps<RLV, 2>, true>(c, rm, in, out, batch, st, mul);                        \
         }                                                                                                               \
-        if (kind == 1) return inverse ? persist_launch<IntInvOps<RLV, 1>>(c, rm, in, out, batch, st)                    \
-                                      : persist_launch<IntFwdOps<RLV, 1>>(c, rm, in, out, batch, st);                   \
-        return inverse ? persist_launch<IntInvOps<RLV, 2>>(c, rm, in, out, batch, st)                                   \
-                       : persist_launch<IntFwdOps<RLV, 2>>(c, rm, in, out, batch, st);
+        if (kind == 1) return inverse ? persist_launch<IntInvOps<RLV, 1>>(c, rm, in, out, batch, st, mul)                    \
+                                      : persist_launch<IntFwdOps<RLV, 1>>(c, rm, in, out, batch, st, mul);                   \
+        return inverse ? persist_launch<IntInvOps<RLV, 2>>(c, rm, in, out, batch, st, mul)                                   \
+                       : persist_launch<IntFwdOps<RLV, 2>>(c, rm, in, out, batch, st, mul);
     switch (rl) {
         PERSIST_CASE(1) PERSIST_CASE(2) PERSIST_CASE(3) PERSIST_CASE(4)
         default: break;

@@ -200,6 +200,12 @@ class Ring:
         f = _lib.lib().lgpu_intt if inverse else _lib.lib().lgpu_ntt
         _lib.check(f(self.ctx.h, self.which, self.level, _dptr(p1), _dptr(p2), lazy, b, bs, _stream()))
 
+    def NTTThenMulCoeffsMontgomery(self, p1, p2, p3):
+        """p3 = MulCoeffsMontgomery(NTT(p1), p2): ring/ntt.go:127-131 + ring/operations.go:88-92 in one pass over HBM."""
+        b, bs = self._batch(p3)
+        self._same_layout(p3, p1, p2)
+        _lib.check(_lib.lib().lgpu_ntt_then_mul_coeffs_montgomery(self.ctx.h, self.which, self.level, _dptr(p1), _dptr(p2), _dptr(p3), b, bs, _stream()))
+
     def NTT(self, p1, p2): self._ntt(False, p1, p2, 0)          # ring/ntt.go:127
     def NTTLazy(self, p1, p2): self._ntt(False, p1, p2, 1)      # ring/ntt.go:134
     def INTT(self, p1, p2): self._ntt(True, p1, p2, 0)          # ring/ntt.go:141

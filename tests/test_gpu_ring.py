@@ -207,3 +207,44 @@ def test_full_size_properties_c2():
         want[i, :k] = (U64(q) - a[i, N - k:]) % U64(q)
     assert np.array_equal(got, want)
     ctx.close()
+
+
+@pytest.mark.parametrize("logN,family", [(13, "ckks"), (16, "ckks"), (16, "q61"), (14, "mixed"), (10, "ckks")])
+def test_ntt_then_mul_coeffs_montgomery_fused(logN, family):
+    """lgpu_ntt_then_mul_coeffs_montgomery == Ring.NTT followed by Ring.MulCoeffsMontgomery (ring/ntt.go:127-131 +
+    ring/operations.go:88-92): the fused last-pass epilogue (2^13..2^16, FP64-pipe and integer rows) and the two-launch
+    fallback (2^10), against the oracle on sampled rows and against the unfused device path on all rows; lazily
+    accumulated inputs above 2^52 included."""
+    lb = _lb()
+    N = 1 << logN
+    if family == "ckks":
+        Q, _ = O.gen_moduli(logN + 1, [56] + [45] * 7, [])
+    elif family == "q61":
+        Q = H.Qi60[:6]
+    else:
+        Q = O.gen_moduli(logN + 1, [56, 45, 45], [])[0] + H.Qi60[:2]
+    ctx = lb.Context(logN, Q)
+    rq = ctx.ringQ
+    rng = np.random.default_rng(logN)
+    batch = 3
+    a = np.stack([H.rand_poly(Q, N, rng) for _ in range(batch)])
+    for i, q in enumerate(Q):
+        if q < (1 << 58):
+            a[0, i, ::7] += U64(1) << U64(62)                       # lazy inputs (NTTStandard accepts any uint64 that does not wrap)
+    b = np.stack([H.rand_poly([(1 << 64) - 1] * len(Q), N, rng) for _ in range(batch)])     # any uint64 multiplicand
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    fused = rq.NewPoly(batch)
+    rq.NTTThenMulCoeffsMontgomery(da, db, fused)
+    ref = rq.NewPoly(batch)
+    rq.NTT(da, ref); rq.MulCoeffsMontgomery(ref, db, ref)
+    assert np.array_equal(ctx.to_host(fused), ctx.to_host(ref))
+    ring = O.Ring(N, Q)
+    want = np.empty_like(a[1]); ring.NTT(a[1], want); ring.MulCoeffsMontgomery(want, b[1], want)
+    assert np.array_equal(ctx.to_host(fused)[1], want)
+    # in place (in == out) and the aliasing error
+    inpl = da.clone()
+    rq.NTTThenMulCoeffsMontgomery(inpl, db, inpl)
+    assert np.array_equal(ctx.to_host(inpl), ctx.to_host(ref))
+    with pytest.raises(lb.LgpuError, match="multiplicand"):
+        rq.NTTThenMulCoeffsMontgomery(da, fused, fused)
+    ctx.close()

@@ -5,7 +5,8 @@ produces the per-config table that DESIGN.md quotes and writes it as JSON (defau
   C1  N=2^12, 1 limb (q = Qi60[0]): NTT then INTT, latency
   C2  N=2^16, 44 limbs (Qi60[0:32] + Pi60[0:12], 61-bit -> integer-pipe kernels) and the same shape with the
       CKKS_L44 45/56-bit primes (FP64-pipe kernels): (i) NTT GB/s, algorithmic bytes 2*S(44);
-      (ii) NTT + MulCoeffsMontgomery, algorithmic bytes 5*S(44) unfused
+      (ii) NTT + MulCoeffsMontgomery, algorithmic bytes 5*S(44) as two calls, 3*S(44) through the fused
+      lgpu_ntt_then_mul_coeffs_montgomery
   C3  CKKS PN16QP1761, batch 64 pairs at level 33: MulRelin + Rescale, ct/s
   C4  BGV N15QP880, batch 128 at level 19: one Galois rotation (Evaluator.Automorphism), ct/s
 """
@@ -93,12 +94,16 @@ def main():
 
                 def ntt_mul():
                     ctx.ringQ.NTT(x, y); ctx.ringQ.MulCoeffsMontgomery(y, w, z)
+                def ntt_mul_fused():
+                    ctx.ringQ.NTTThenMulCoeffsMontgomery(x, w, z)
                 m1, _ = timeit(ntt, args.iters, 3, flush)
                 m2, _ = timeit(ntt_mul, args.iters, 3, flush)
+                m3, _ = timeit(ntt_mul_fused, args.iters, 3, flush)
                 res["C2_%s_batch%d" % (tag, batch)] = {
                     "workload": "N=65536 l=44 (%s primes), %d polynomial(s) per call" % (tag, batch),
                     "ntt_us": m1 * 1e6, "ntt_alg_GBs": 2 * S * batch / m1 / 1e9,
                     "ntt_mul_us": m2 * 1e6, "ntt_mul_alg_GBs_unfused": 5 * S * batch / m2 / 1e9,
+                    "ntt_mul_fused_us": m3 * 1e6, "ntt_mul_fused_alg_GBs": 3 * S * batch / m3 / 1e9, "ntt_mul_fused_speedup": m2 / m3,
                     "us_per_limb_ntt": m1 * 1e6 / (nl * batch)}
             ctx.close()
 
