@@ -248,6 +248,12 @@ __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStri
         const u64 s0 = p.s0[blockIdx.y];
 #pragma unroll
         for (int k = 0; k < R; k++) e[k] = cred(bc[k * stride + l] + p.bc_add, p.bc_q) + s0;
+        // a wide last modulus under a narrow row (mixed 40 / 60-bit chains): bring the value into the range the butterflies
+        // assume (< 2^52 for the FP64 rows, < 8q for the integer ones); only its residue matters
+        if (p.bc_q >> 50) {
+#pragma unroll
+            for (int k = 0; k < R; k++) e[k] = bred_add(e[k], q, L.bred_hi);
+        }
     } else {
     const bool multi = nS > 1 || !p.single_rule;
     const u64 half_t = multi ? p.blob[dg.off_half_t + limb] : 0;
@@ -294,14 +300,16 @@ __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStri
         for (int k = 0; k < R; k++) out[(size_t)k * stride + l] = (u64)__double_as_longlong(x[k]);
     } else {
         const ulonglong2* tw = L.tw_fwd;
-        const u64 nq = 0ull - q, twoq = q << 1;
+        const u64 nq = 0ull - q, twoq = q << 1, kq = L.kq;
+        const unsigned mask = L.fwd_mask;     // per-prime lazy-correction schedule (0 below 2^57; every stage for 61-bit primes)
 #pragma unroll
         for (int u = 0; u < RL; u++) {
             const int half = 1 << (RL - 1 - u);
+            const bool corr = (mask >> u) & 1u;
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 if (k & half) continue;
-                fast_fwd_bfly(e[k], e[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), nq, twoq, 0, false);
+                fast_fwd_bfly(e[k], e[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), nq, twoq, kq, corr);
             }
         }
 #pragma unroll
@@ -395,14 +403,16 @@ __global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(
         for (int k = 0; k < R; k++) out[(size_t)k * stride] = (u64)__double_as_longlong(x[k]);
     } else {
         const ulonglong2* tw = L.tw_fwd;
-        const u64 nq = 0ull - q, twoq = q << 1;
+        const u64 nq = 0ull - q, twoq = q << 1, kq = L.kq;
+        const unsigned mask = L.fwd_mask;     // per-prime lazy-correction schedule (0 below 2^57; every stage for 61-bit primes)
 #pragma unroll
         for (int u = 0; u < RL; u++) {
             const int half = 1 << (RL - 1 - u);
+            const bool corr = (mask >> u) & 1u;
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 if (k & half) continue;
-                fast_fwd_bfly(e[k], e[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), nq, twoq, 0, false);
+                fast_fwd_bfly(e[k], e[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), nq, twoq, kq, corr);
             }
         }
 #pragma unroll
@@ -501,21 +511,22 @@ __global__ void __launch_bounds__(256, 2) ks_chunk_mac_kernel(KsChunkParams p) {
                     for (int u = 0; u < 4; u++) {
                         const int half = 1 << (3 - u);
                         const int twbase = (1 << (s1 + u)) + (chunk << u);
+                        const bool corr = (L.fwd_mask >> (s1 + u)) & 1u;
 #pragma unroll
                         for (int k = 0; k < 16; k++) {
                             if (k & half) continue;
-                            fast_fwd_bfly(raw[k], raw[k + half], __ldg(tw + twbase + (k >> (4 - u))), nq, twoq, 0, false);
+                            fast_fwd_bfly(raw[k], raw[k + half], __ldg(tw + twbase + (k >> (4 - u))), nq, twoq, L.kq, corr);
                         }
                     }
 #pragma unroll
                     for (int k = 0; k < 16; k++) sm[pad_idx(k * T + tid)] = raw[k];
                 }
                 __syncthreads();
-                fwd_round<CL, 4, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+                fwd_round<CL, 4, 4, false, 1>(sm, nullptr, L, s1, p.logN, chunk, tid);
 #pragma unroll
                 for (int j = 0; j < 8; j++) { k0[j] = __ldg(e0 + j * T + tid); k1[j] = __ldg(e1 + j * T + tid); }
                 __syncthreads();
-                fwd_round<CL, 8, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+                fwd_round<CL, 8, 4, false, 1>(sm, nullptr, L, s1, p.logN, chunk, tid);
             }
             __syncthreads();
         } else {
@@ -737,9 +748,9 @@ bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
     if (evk.levelP < 1 || evk.pw2 != 0) return false;          // multiple-P path only
     const int k = evk.levelP + 1;
     const int nd = base_rns_decomposition_vector_size(levelQ, evk.levelP);
-    if (levelQ + 1 > 64 || nd > kMaxDigits || k > 4) return false;   // digit sizes validated on the device: 2..4 (larger k takes the unfused kernels)
-    for (int i = 0; i <= levelQ; i++) if (!c->h_limbs[i].fp_ok && c->h_limbs[i].fwd_mask != 0) return false;
-    for (int j = 0; j <= evk.levelP; j++) if (!c->h_limbs[c->nQ + j].fp_ok && c->h_limbs[c->nQ + j].fwd_mask != 0) return false;
+    // digit sizes 2..6 (the reference's parameter sets use up to 6 special primes: circuits/ckks/bootstrapping/default_parameters.go:118-134);
+    // the 128-bit sum of ks_ext holds k products of a source word and a target constant: k * 2^61 * t < t * 2^64 needs k < 8
+    if (levelQ + 1 > 64 || nd > kMaxDigits || k > 6) return false;
     return true;
 }
 
@@ -940,11 +951,11 @@ __global__ void __launch_bounds__(256, 2) fz_chunk_epi_kernel(FzChunkParams p) {
         __syncthreads();
         fp_fwd_round_tw<CL, 8, 4>(fsm, t3, L.fq, L.fqinv, tid);
     } else {
-        fwd_round<CL, 0, 4, true, 2>(sm, src, L, s1, p.logN, chunk, tid);
+        fwd_round<CL, 0, 4, true, 1>(sm, src, L, s1, p.logN, chunk, tid);
         __syncthreads();
-        fwd_round<CL, 4, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+        fwd_round<CL, 4, 4, false, 1>(sm, nullptr, L, s1, p.logN, chunk, tid);
         __syncthreads();
-        fwd_round<CL, 8, 4, false, 2>(sm, nullptr, L, s1, p.logN, chunk, tid);
+        fwd_round<CL, 8, 4, false, 1>(sm, nullptr, L, s1, p.logN, chunk, tid);
     }
     __syncthreads();
     // loads of a whole batch are issued before any store (out may alias A or D, so the compiler cannot hoist them itself)
@@ -1070,8 +1081,7 @@ static void split_rows(const Ctx* c, int limb0, int nrows, RowMap& fp, RowMap& i
 bool fz_applicable(const Ctx* c, int levelQ, int levelP) {
     static const int off = [] { const char* e = getenv("LGPU_NO_FUSED_KS"); return e && atoi(e) ? 1 : 0; }();
     if (off || c->ring_type != 0 || c->logN < 13 || c->logN > 16) return false;
-    if (levelQ + 1 > kMaxRows || levelP + 1 > 4) return false;   // validated source counts only
-    for (int i = 0; i <= levelQ; i++) if (!c->h_limbs[i].fp_ok && c->h_limbs[i].fwd_mask != 0) return false;
+    if (levelQ + 1 > kMaxRows || levelP + 1 > 6) return false;   // source counts 1..6 (see ks_fused_applicable)
     return true;
 }
 

@@ -136,3 +136,42 @@ def test_ntt_accepts_words_above_2_52():
         ctx.ringQ.NTT(d, o)
         assert np.array_equal(ctx.to_host(o), want), logN
         ctx.close()
+
+
+def test_fused_keyswitch_wide_primes_and_k5_k6():
+    """The fused pipeline on what the reference's bootstrapping literals need (VERDICT r1 item 5;
+    circuits/ckks/bootstrapping/default_parameters.go:118-134): 61-bit special primes (integer rows that need the lazy
+    correction schedule at every stage), k = 5 and k = 6, chains that mix 40-bit FP64-pipe rows with 56/60-bit integer rows,
+    full / ragged / single-limb last digits. N = 2^13 (smallest fused size) against the oracle."""
+    lb = _lb()
+    q = O.gen_moduli(14, [60, 40, 40, 40, 39, 60, 60, 56, 56, 40, 40], [])[0]
+    p6 = O.gen_moduli(14, [], [61] * 6)[1]
+    _gadget_case(lb, 13, q, p6, 0, (10, 7, 6, 5), batch=2, seed=71)        # k = 6: digits 6+5, 6+2, 6+1 (single-limb last digit), 6
+    _gadget_case(lb, 13, q, p6[:5], 0, (10, 9, 4), batch=2, seed=72)      # k = 5: 5+5+1, 5+5, 5
+    _gadget_case(lb, 13, H.Qi60[:7], H.Pi60[:3], 0, (6, 5, 3), batch=2, seed=73)   # all rows 61-bit
+
+
+def test_boot_chain_keyswitch_and_mulrelin_logn16():
+    """N16QP1767H32768H32's chain at full size (30 Q limbs: 60 + 13x40 + 3x39 + 9x60 + 4x56 bits, 6 x 61-bit P limbs, beta = 5):
+    gadget product at the top level and at an EvalMod level, plus MulRelin + Rescale, against the oracle."""
+    import torch
+    lb = _lb()
+    from lattigo_b200 import params as presets
+    s = presets.PRESETS["BOOT_N16QP1767"]
+    logN, q, p = s["logN"], s["Q"], s["P"]
+    _gadget_case(lb, logN, q, p, 0, (29, 20), batch=1, seed=81)
+    ctx = lb.Context(logN, q, p)
+    N = 1 << logN
+    level, levelP = 25, len(p) - 1                           # a rescale from a 60-bit last modulus over 40-bit rows
+    params = O.Parameters(logN, q, p)
+    nd = params.BaseRNSDecompositionVectorSize(len(q) - 1, levelP)
+    g = torch.Generator(device="cuda"); g.manual_seed(82)
+    evk_t = _torch_rand_rows(N, q + p, (nd, 1, 2), g)
+    ev = lb.CKKSEvaluator(ctx, lb.GadgetCiphertext(ctx, evk_t, len(q) - 1, levelP))
+    a = _torch_rand_rows(N, q[: level + 1], (2, 2), g); b = _torch_rand_rows(N, q[: level + 1], (2, 2), g)
+    out = ev.MulRelinRescaleNew(a, b)
+    ev_o = O.CKKSEvaluator(params, O.GadgetCiphertext(ctx.to_host(evk_t), len(q), levelP + 1))
+    ah, bh, oh = ctx.to_host(a), ctx.to_host(b), ctx.to_host(out)
+    r = ev_o.Rescale(ev_o.MulRelinNew([ah[0, 0], ah[0, 1]], [bh[0, 0], bh[0, 1]]))
+    assert np.array_equal(oh[0, 0], r[0]) and np.array_equal(oh[0, 1], r[1])
+    ctx.close()
