@@ -974,7 +974,12 @@ __global__ void __launch_bounds__(256, 2) fz_chunk_epi_kernel(FzChunkParams p) {
             const int idx = (k0 + j) * T + tid;
             u64 x;
             if (FP) x = fp_canon(reinterpret_cast<double*>(sm)[fpad(idx)], L.fq, L.fqinv);
-            else x = sm[pad_idx(idx)];
+            else {
+                // lazy transform output: below 2 kq, i.e. up to ~2^64 for 60/61-bit primes -- one correction keeps x + 2q - a
+                // inside 64 bits (kq is a multiple of q)
+                x = sm[pad_idx(idx)];
+                x = x >= L.kq ? x - L.kq : x;
+            }
             u64 r = mred(x + twoq - a[j], sc, q, qinv);
             if (D) r = cred(r + d[j], q);
             out[idx] = r;

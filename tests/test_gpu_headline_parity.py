@@ -159,7 +159,7 @@ def test_boot_chain_keyswitch_and_mulrelin_logn16():
     from lattigo_b200 import params as presets
     s = presets.PRESETS["BOOT_N16QP1767"]
     logN, q, p = s["logN"], s["Q"], s["P"]
-    _gadget_case(lb, logN, q, p, 0, (29, 20), batch=1, seed=81)
+    _gadget_case(lb, logN, q, p, 0, (29, 23, 20), batch=1, seed=81)
     ctx = lb.Context(logN, q, p)
     N = 1 << logN
     level, levelP = 25, len(p) - 1                           # a rescale from a 60-bit last modulus over 40-bit rows
