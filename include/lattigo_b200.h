@@ -291,6 +291,48 @@ int lgpu_evaluator_automorphism_hoisted_lazy(lgpu_ctx* ctx, int level_q, const u
                                              uint64_t gal_el, const lgpu_gadget_ct* gk, uint64_t* out0q, uint64_t* out0p, uint64_t* out1q,
                                              uint64_t* out1p, int batch, size_t stride_ct, size_t stride_q, size_t stride_p, void* stream);
 
+/* ---- RGSW (core/rgsw) --------------------------------------------------------------------------------------------------
+ * rgsw.Evaluator.ExternalProduct (core/rgsw/evaluator.go:39-88): RLWE x RGSW -> RLWE at the RGSW ciphertext's levels.
+ * rgsw0 / rgsw1 = rgsw.Ciphertext.Value[0] / Value[1] (core/rgsw/elements.go:11-13). ct_in: [batch][2][level_in+1][N], NTT domain;
+ * ct_out: [batch][2][level_out+1][N], rows 0..rgsw level written; ct_out == ct_in allowed (how the reference's callers use it).
+ * All three reference paths (multiple P :210-283, single P / bit decomposition :130-208, 32-bit :90-128) are covered. */
+int lgpu_rgsw_external_product(lgpu_ctx* ctx, const uint64_t* ct_in, int level_in, const lgpu_gadget_ct* rgsw0,
+                               const lgpu_gadget_ct* rgsw1, uint64_t* ct_out, int level_out, int batch, void* stream);
+
+/* ---- encryptor / key-generator inner loops and device samplers (core/rlwe/encryptor.go, keygenerator.go, ring/sampler_*.go) ----
+ * Samplers: the reference's distributions on Philox4x32-10 counter streams keyed by (seed, stream_id) -- NOT the reference's
+ * blake2b-XOF byte stream (sampling/prng.go), which is inherently sequential. Small polynomials are int64 vectors [batch][N]. */
+/* ringqp.UniformSampler.Read (ring/sampler_uniform.go:48-100): rows 0..level uniform in [0, q_i). */
+int lgpu_sample_uniform(lgpu_ctx* ctx, int ring, int level, uint64_t seed, uint64_t stream_id, uint64_t* out, int batch,
+                        size_t batch_stride, void* stream);
+/* ring.TernarySampler (ring/sampler_ternary.go): hamming_weight > 0 selects ring.Ternary{H} (exactly H non-zero coefficients),
+ * otherwise ring.Ternary{P = p} (P(+1) = P(-1) = p / 2). */
+int lgpu_sample_ternary(lgpu_ctx* ctx, double p, int hamming_weight, uint64_t seed, uint64_t stream_id, int64_t* out, int batch,
+                        void* stream);
+/* ring.GaussianSampler (ring/sampler_gaussian.go:160-182): round(|N(0,1)| sigma) with a random sign, |.| <= bound. */
+int lgpu_sample_gaussian(lgpu_ctx* ctx, double sigma, double bound, uint64_t seed, uint64_t stream_id, int64_t* out, int batch,
+                         void* stream);
+/* What Sampler.Read + ringqp.Ring.ExtendBasisSmallNormAndCenter (ring/ringqp/operations.go:325-351) leave in a ringqp.Poly:
+ * the signed value modulo every q_i (out_q, level_q+1 rows) and p_j (out_p, level_p+1 rows); either output may be NULL. */
+int lgpu_small_poly_to_rns(lgpu_ctx* ctx, int level_q, int level_p, const int64_t* small, uint64_t* out_q, uint64_t* out_p,
+                           int batch, size_t stride_q, size_t stride_p, void* stream);
+/* Encryptor.encryptZeroPk for a plain rlwe.Ciphertext (core/rlwe/encryptor.go:204-299: one special prime, ModDownQPtoQ) or, when
+ * the context has no P, encryptZeroPkNoP (:301-341). pk: rlwe.PublicKey.Value = [2][nQ + nP][N] at the maximum levels (NTT +
+ * Montgomery); u (xs sample), e0, e1 (xe samples): [batch][N]; ct_out: [batch][2][level_q+1][N]. */
+int lgpu_encrypt_zero_pk(lgpu_ctx* ctx, int level_q, const uint64_t* pk, const int64_t* u, const int64_t* e0, const int64_t* e1,
+                         uint64_t* ct_out, int is_ntt, int is_montgomery, int batch, void* stream);
+/* Encryptor.encryptZeroSkFromC1QP (:404-430; level_p = -1 for a plain ciphertext): c0 = e - c1 * sk. sk: [nQ + nP][N]; c1, c0:
+ * [batch][level_q+1 + level_p+1][N] (Q rows then P rows); c1 is the uniform polynomial in the NTT domain (rewritten by INTT only
+ * when !is_ntt, like the reference). */
+int lgpu_encrypt_zero_sk(lgpu_ctx* ctx, int level_q, int level_p, const uint64_t* sk, uint64_t* c1, const int64_t* e, uint64_t* c0,
+                         int is_ntt, int is_montgomery, int batch, void* stream);
+/* KeyGenerator.genEvaluationKey (core/rlwe/keygenerator.go:287-330) + AddPolyTimesGadgetVectorToGadgetCiphertext
+ * (core/rlwe/gadgetciphertext.go:171-241) at the maximum levels. On entry component 1 of every evk->data[i][j] holds the uniform
+ * polynomial (e.g. from lgpu_sample_uniform; evk->data is written although the struct declares it const); e: [n_digits][n_pw2_max][N]
+ * error samples; sk_in: [nQ][N], sk_out: [nQ + nP][N], NTT + Montgomery. */
+int lgpu_gen_evaluation_key(lgpu_ctx* ctx, const uint64_t* sk_in, const uint64_t* sk_out, lgpu_gadget_ct* evk, const int64_t* e,
+                            void* stream);
+
 /* ---- wire format -> device (the reference's WriteTo / ReadFrom byte streams, little-endian uint64 words) ------------------
  * ring.Poly (ring/poly.go:132-179): rows, then per row {len, len words}. */
 int lgpu_poly_load(lgpu_ctx* ctx, const void* bytes, size_t nbytes, uint64_t* dst, int rows_cap, int* rows_out, size_t* consumed,

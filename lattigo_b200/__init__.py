@@ -9,3 +9,5 @@ from .rlwe import (GadgetCiphertext, BasisExtender, Decomposer, Evaluator, CKKSE
 from .ringqp import RingQP, Poly as PolyQP  # noqa: F401
 from . import lintrans  # noqa: F401,E402
 from . import wire  # noqa: F401,E402
+from . import rgsw  # noqa: F401,E402
+from . import encryptor  # noqa: F401,E402

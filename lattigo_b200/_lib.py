@@ -81,6 +81,14 @@ def lib():
             "lgpu_ckks_mulrelin_rescale_batch_host": [vp, i, vp, vp, vp, i, vp, i, i],
             "lgpu_lintrans_evaluate_many": [vp, i, vp, vp, i, vp, vp, vp, i, vp],
             "lgpu_evaluator_automorphism_hoisted_lazy": [vp, i, vp, vp, i, u64, vp, vp, vp, vp, vp, i, z, z, z, vp],
+            "lgpu_rgsw_external_product": [vp, vp, i, vp, vp, vp, i, i, vp],
+            "lgpu_sample_uniform": [vp, i, i, u64, u64, vp, i, z, vp],
+            "lgpu_sample_ternary": [vp, c.c_double, i, u64, u64, vp, i, vp],
+            "lgpu_sample_gaussian": [vp, c.c_double, c.c_double, u64, u64, vp, i, vp],
+            "lgpu_small_poly_to_rns": [vp, i, i, vp, vp, vp, i, z, z, vp],
+            "lgpu_encrypt_zero_pk": [vp, i, vp, vp, vp, vp, vp, i, i, i, vp],
+            "lgpu_encrypt_zero_sk": [vp, i, i, vp, vp, vp, vp, i, i, i, vp],
+            "lgpu_gen_evaluation_key": [vp, vp, vp, vp, vp, vp],
             "lgpu_poly_load": [vp, vp, z, vp, i, vp, vp, vp],
             "lgpu_poly_store": [vp, vp, i, vp, z, vp, vp],
             "lgpu_gadget_ct_load": [vp, vp, z, vp, z, vp, vp],

@@ -55,6 +55,22 @@ int lgpu_lintrans_evaluate_many(lgpu_ctx* ctx, int level_in, const uint64_t* ct_
     return lintrans_evaluate_many(&ctx->c, level_in, (const u64*)ct_in, mv.data(), n_mats, ks, (u64* const*)ct_outs, out_levels, batch, S(stream));
 }
 
+int lgpu_rgsw_external_product(lgpu_ctx* ctx, const uint64_t* ct_in, int level_in, const lgpu_gadget_ct* rgsw0, const lgpu_gadget_ct* rgsw1,
+                               uint64_t* ct_out, int level_out, int batch, void* stream) {
+    REQUIRE_DEVICE(ctx);
+    REQUIRE(ct_in && ct_out, "null ciphertext");
+    REQUIRE_ALIGNED(AL(ct_in) && AL(ct_out));
+    REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
+    GadgetCt g0, g1;
+    if (to_gct3(rgsw0, g0) || to_gct3(rgsw1, g1)) return -1;
+    REQUIRE(g0.levelQ >= 0 && g0.levelQ <= level_in && g0.levelQ <= level_out, "RGSW ciphertext level above the RLWE ciphertexts' level");
+    const size_t N = ctx->c.N, ci = (size_t)(level_in + 1) * N, co = (size_t)(level_out + 1) * N;
+    const u64* in = (const u64*)ct_in;
+    u64* out = (u64*)ct_out;
+    return rgsw_external_product(&ctx->c, g0, g1, CSpan{in, N, 2 * ci}, CSpan{in + ci, N, 2 * ci}, Span{out, N, 2 * co}, Span{out + co, N, 2 * co}, batch,
+                                 S(stream));
+}
+
 int lgpu_evaluator_automorphism_hoisted_lazy(lgpu_ctx* ctx, int level_q, const uint64_t* ct0, const uint64_t* decomp, int decomp_level_q,
                                              uint64_t gal_el, const lgpu_gadget_ct* gk, uint64_t* out0q, uint64_t* out0p, uint64_t* out1q,
                                              uint64_t* out1p, int batch, size_t stride_ct, size_t stride_q, size_t stride_p, void* stream) {

@@ -413,7 +413,11 @@ static int gadget_product_multiple_p_lazy(const Ctx* c, int levelQ, CSpan cx, co
 }
 
 // gadgetProductSinglePAndBitDecompLazy, core/rlwe/evaluator_gadget_product.go:203-338 (levelP <= 0)
-static int gadget_product_single_p_lazy(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st) {
+// rgsw_mode (core/rgsw/evaluator.go:130-208): the digit is ALWAYS MaskVec(limb i, j*pw2, mask) with mask = 2^64-1 when pw2 == 0 (the raw,
+// uncentred limb -- not the Decomposer's single-limb rule), and the accumulation runs over both components of the RGSW ciphertext
+// (acc_first / acc_last tell which call opens and which one closes it).
+static int gadget_product_single_p_lazy(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st,
+                                        bool rgsw_mode = false, bool acc_first = true, bool acc_last = true) {
     const int levelP = evk.levelP;
     const size_t N = c->N, nq = levelQ + 1, np = levelP + 1;
     Scratch buf;
@@ -424,7 +428,7 @@ static int gadget_product_single_p_lazy(const Ctx* c, int levelQ, CSpan cx, cons
     Span c2P{c2 + nq * N, N, (nq + np) * N};
     if (launch_intt(c, rows_range(0, 0, (int)nq), cx, cxInv, batch, NTT_CANONICAL, st)) return -1;
     const int pw2 = evk.pw2;
-    const u64 mask = pw2 ? ((1ull << pw2) - 1) : 0;
+    const u64 mask = pw2 ? ((1ull << pw2) - 1) : (rgsw_mode ? ~0ull : 0);
     const RowMap rqp = rows_qp(c, (int)nq, (int)np);
     int total = 0;
     for (int i = 0; i <= levelQ; i++) total += evk.pw2_sizes ? evk.pw2_sizes[i] : 1;
@@ -441,7 +445,12 @@ static int gadget_product_single_p_lazy(const Ctx* c, int levelQ, CSpan cx, cons
                 if (launch_vecop(c, rqp, LGPU_OP_MASK, src, CSpan{nullptr, 0, 0}, Span{c2, N, (nq + np) * N}, batch, nullptr, nullptr,
                                  (u64)(j * pw2), mask, c->N, st)) return -1;
             }
-            if (launch_ntt(c, rqp, CSpan{c2, N, (nq + np) * N}, Span{c2, N, (nq + np) * N}, batch, NTT_EXACT_LAZY, st)) return -1;
+            if (mask == ~0ull) {
+                // a raw limb of another prime (up to 61 bits) under every modulus: reduce first, the transforms assume lazily reduced input
+                if (launch_vecop(c, rqp, LGPU_OP_REDUCE, CSpan{c2, N, (nq + np) * N}, CSpan{nullptr, 0, 0}, Span{c2, N, (nq + np) * N}, batch, nullptr, nullptr,
+                                 0, 0, c->N, st)) return -1;
+                if (launch_ntt(c, rqp, CSpan{c2, N, (nq + np) * N}, Span{c2, N, (nq + np) * N}, batch, NTT_CANONICAL, st)) return -1;
+            } else if (launch_ntt(c, rqp, CSpan{c2, N, (nq + np) * N}, Span{c2, N, (nq + np) * N}, batch, NTT_EXACT_LAZY, st)) return -1;
             MacParams m;
             memset(&m, 0, sizeof(m));
             m.limbs = c->d_limbs; m.evk0 = evk.at(i, j, 0, N); m.evk1 = evk.at(i, j, 1, N); m.nQk = evk.levelQ + 1;
@@ -450,7 +459,7 @@ static int gadget_product_single_p_lazy(const Ctx* c, int levelQ, CSpan cx, cons
             for (int k = 0; k < 2; k++) { m.accQ[k] = acc.q[k].p; m.accP[k] = acc.p[k].p; }
             m.accQ_rs = acc.q[0].row_stride; m.accQ_bs = acc.q[0].batch_stride; m.accP_rs = acc.p[0].row_stride; m.accP_bs = acc.p[0].batch_stride;
             m.nq = (int)nq; m.np = (int)np; m.nQfull = c->nQ;
-            m.first = (done == 0); m.last = (done == total - 1); m.batch = batch; m.n = c->N;
+            m.first = acc_first && (done == 0); m.last = acc_last && (done == total - 1); m.batch = batch; m.n = c->N;
             if (launch_mac(m, st)) return -1;
             done++;
         }
@@ -524,6 +533,43 @@ int gadget_product(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, Span
     }
     if (gadget_product_lazy(c, levelQ, cx, evk, acc, batch, st)) return -1;
     return evaluator_moddown_ntt(c, levelQ, levelP, acc, ct0, ct1, batch, st);
+}
+
+// rgsw.Evaluator.ExternalProduct (core/rgsw/evaluator.go:39-88): out = ModDown( <decomp(ct[0]), rgsw[0]> + <decomp(ct[1]), rgsw[1]> ) at the
+// RGSW ciphertext's levels; NTT-domain RLWE ciphertext; out may alias ct (the way both of the reference's callers use it,
+// core/rgsw/rgsw_test.go:84, core/rgsw/blindrot/evaluator.go:212). The three reference code paths leave the same canonical residues:
+//   levelP >= 1   externalProductInPlaceMultipleP (:210-283)            = two lazy gadget products (fused pipeline where it applies)
+//   levelP <  1   externalProductInPlaceSinglePAndBitDecomp (:130-208)  = mask / raw-limb digits, Montgomery MAC
+//   32-bit case   externalProduct32Bit (:90-128) + IMForm               = the same sum: IMForm(sum key * x) == sum MRed(key, x)
+int rgsw_external_product(const Ctx* c, const GadgetCt& rg0, const GadgetCt& rg1, CSpan ct0, CSpan ct1, Span out0, Span out1, int batch, cudaStream_t st) {
+    const int levelQ = rg0.levelQ, levelP = rg0.levelP;
+    if (rg1.levelQ != levelQ || rg1.levelP != levelP || rg1.pw2 != rg0.pw2) { set_error("RGSW ciphertext: the two gadget ciphertexts differ in level or base"); return -1; }
+    if (check_evk(c, levelQ, rg0) || check_evk(c, levelQ, rg1)) return -1;
+    const size_t N = c->N, nq = levelQ + 1, np = levelP + 1;
+    Scratch buf;
+    const size_t per = (size_t)2 * batch * (nq + np) * N;
+    if (buf.alloc(2 * per, st)) return -1;
+    auto stacked = [&](u64* base) {
+        AccSpans a;
+        for (int k = 0; k < 2; k++) {
+            u64* b = base + (size_t)k * batch * (nq + np) * N;
+            a.q[k] = Span{b, N, (nq + np) * N};
+            a.p[k] = Span{b + nq * N, N, (nq + np) * N};
+        }
+        return a;
+    };
+    AccSpans A = stacked(buf.p), B = stacked(buf.p + per);
+    if (levelP >= 1) {
+        if (rg0.pw2 != 0) { set_error("RGSW external product: BaseTwoDecomposition != 0 requires levelP <= 0"); return -1; }
+        if (gadget_product_multiple_p_lazy(c, levelQ, ct0, rg0, A, batch, st)) return -1;
+        if (gadget_product_multiple_p_lazy(c, levelQ, ct1, rg1, B, batch, st)) return -1;
+        if (launch_vecop(c, rows_qp(c, (int)nq, (int)np), LGPU_OP_ADD, CSpan{buf.p, N, (nq + np) * N}, CSpan{buf.p + per, N, (nq + np) * N},
+                         Span{buf.p, N, (nq + np) * N}, 2 * batch, nullptr, nullptr, 0, 0, c->N, st)) return -1;
+    } else {
+        if (gadget_product_single_p_lazy(c, levelQ, ct0, rg0, A, batch, st, true, true, false)) return -1;
+        if (gadget_product_single_p_lazy(c, levelQ, ct1, rg1, A, batch, st, true, false, true)) return -1;
+    }
+    return evaluator_moddown_ntt(c, levelQ, levelP, A, out0, out1, batch, st);
 }
 
 // DecomposeNTT (:459-483): decomp = [digit][batch?]... layout: decomp[digit] is a QP-stacked poly

@@ -62,6 +62,7 @@ int decompose_ntt(const Ctx* c, int levelQ, int levelP, int nbPi, CSpan c2, bool
 int gadget_product_lazy(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st);
 int evaluator_moddown_ntt(const Ctx* c, int levelQ, int levelP, const AccSpans& acc, Span ct0, Span ct1, int batch, cudaStream_t st);
 int gadget_product(const Ctx* c, int levelQ, CSpan cx, const GadgetCt& evk, Span ct0, Span ct1, int batch, cudaStream_t st);
+int rgsw_external_product(const Ctx* c, const GadgetCt& rg0, const GadgetCt& rg1, CSpan ct0, CSpan ct1, Span out0, Span out1, int batch, cudaStream_t st);
 // decomp_levelQ: level the DecomposeNTT buffer was laid out for (>= levelQ; -1 = levelQ) -- lintrans uses one decomposition for matrices of lower levels
 int gadget_product_hoisted_lazy(const Ctx* c, int levelQ, const u64* decomp, const GadgetCt& evk, const AccSpans& acc, int batch, cudaStream_t st,
                                 int decomp_levelQ = -1);

@@ -152,3 +152,34 @@ def marshal_gadget_ct(gct: "O.GadgetCiphertext") -> bytes:
 def marshal_galois_key(gal_el: int, nth_root: int, gct) -> bytes:
     """rlwe.GaloisKey.MarshalBinary (core/rlwe/keys.go:628-657)."""
     return np.array([gal_el, nth_root], dtype="<u8").tobytes() + marshal_gadget_ct(gct)
+
+
+def gen_rgsw(params: "O.Parameters", m1, s, rng, pw2=0):
+    """Real RGSW encryption of the small polynomial m1 under s (core/rgsw/encryptor.go:34-88 + elements.go:11-13):
+    Value[0] = gadget encryption of m1 (message on component 0), Value[1] = gadget encryption of zero with
+    P * w^j * m1 added to component 1 on the digit's own limbs (i.e. of m1 * s)."""
+    v0 = gen_switching_key(params, m1, s, rng, pw2=pw2)
+    v1 = gen_switching_key(params, [0] * params.N(), s, rng, pw2=pw2)
+    levelQ, levelP = params.MaxLevelQ(), params.MaxLevelP()
+    Qm, Pm = params.qi, params.pi
+    mods = Qm + Pm
+    m_ntt = np.empty((len(mods), params.N()), dtype=U64)
+    rows = small_poly_rns(m1, mods)
+    params.ringQ.NTT(rows[: levelQ + 1], m_ntt[: levelQ + 1])
+    if params.ringP is not None:
+        params.ringP.NTT(rows[levelQ + 1:], m_ntt[levelQ + 1:])
+    Pprod = 1
+    for p in Pm:
+        Pprod *= p
+    kP = max(levelP + 1, 1)
+    R = 1 << 64
+    for i in range(v1.data.shape[0]):
+        for j in range(v1.pw2_sizes[i]):
+            for k in range(kP):
+                idx = i * kP + k
+                if idx >= levelQ + 1:
+                    break
+                q = Qm[idx]
+                f = Pprod * (1 << (pw2 * j)) % q * R % q          # Montgomery form, like the key rows
+                v1.data[i, j, 1, idx] = np.array([(int(x) + f * int(y)) % q for x, y in zip(v1.data[i, j, 1, idx], m_ntt[idx])], dtype=U64)
+    return [v0, v1]

@@ -138,6 +138,25 @@ def main():
                      "ct_per_s": batch / med, "alg_bytes_per_batch": alg, "alg_GBs": alg / med / 1e9}
         ctx.close()
 
+    if on("BOOT"):
+        P = presets.PRESETS["BOOT_N16QP1767"]
+        ctx = lb.Context(16, P["Q"], P["P"])
+        level, levelP, batch = len(P["Q"]) - 1, len(P["P"]) - 1, 32
+        evk = lb.GadgetCiphertext(ctx, rand_evk(ctx, level, levelP, rng, dev), level, levelP)
+        ev = lb.CKKSEvaluator(ctx, evk)
+        for lv in (level, 25):
+            a = rand_rows(ctx.Q[: lv + 1], ctx.N, batch * 2, rng, dev).view(batch, 2, lv + 1, ctx.N)
+            b = rand_rows(ctx.Q[: lv + 1], ctx.N, batch * 2, rng, dev).view(batch, 2, lv + 1, ctx.N)
+            med, mn = timeit(lambda: ev.MulRelinRescaleNew(a, b), args.iters, 3, flush)
+            nd_lv = (lv + levelP + 1) // (levelP + 1)
+            res["BOOT_level%d" % lv] = {"workload": "N16QP1767H32768H32 chain (30 Q limbs 60/40/39/60/56 bits, 6 x 61-bit P), batch 32 pairs at level %d: MulRelin + Rescale" % lv,
+                                        "ms_per_batch": med * 1e3, "ct_per_s": batch / med, "digits": nd_lv,
+                                        "us_per_ct_per_row_digit": med * 1e6 / batch / ((lv + 1 + levelP + 1) * nd_lv)}
+        ctx.close()
+        # the same cost figure for the 45-bit chain (C3) is C3.ms_per_batch / 64 / ((34 + 4) * 9)
+        if "C3" in res:
+            res["C3"]["us_per_ct_per_row_digit"] = res["C3"]["ms_per_batch"] * 1e3 / 64 / (38 * 9)
+
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(res, f, indent=1)
