@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="ciphertext pairs per pipeline chunk of the host entry point (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mulrelin", choices=["mulrelin", "bootstrap"],
+                    help="bootstrap: BASELINE config 5 -- replay of the op trace of one CKKS bootstrapping (use --preset BOOT_N16QP1767)")
     return ap.parse_args()
 
 
@@ -406,8 +408,95 @@ def gpu_main(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------------
+# BASELINE config 5: CKKS bootstrapping throughput by op-trace replay (lattigo_b200/boottrace.py + bootreplay.py)
+# ----------------------------------------------------------------------------------------------------------
+def bootstrap_main(args):
+    import torch
+    import torch.distributed as dist
+    import lattigo_b200 as lb
+    from lattigo_b200 import params as presets, _lib, boottrace
+    from lattigo_b200.bootreplay import BootstrapReplay
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "no CPU restatement of circuits/ckks/bootstrapping exists in oracle/ (Go is not installed); "
+                              "the bootstrap workload is an op-trace replay of the device path only"}))
+        return 0
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    s = presets.PRESETS[args.preset]
+    ctx = lb.Context(s["logN"], s["Q"], s["P"], device=local)
+    g = torch.Generator(device=dev); g.manual_seed(2000 + rank)
+    n_res = 14 if args.preset == "BOOT_N16QP1767" else max(1, len(s["Q"]) - 16)
+    trace = boottrace.bootstrap_trace(logN=s["logN"], residual_limbs=n_res)
+    rep = BootstrapReplay(ctx, args.batch, g, trace)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        rep.run()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib().lgpu_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    phases = {}
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        ms, nops = rep.run()
+        for k, v in ms.items():
+            phases[k] = phases.get(k, 0.0) + v
+    e1.record()
+    barrier()
+    launches = _lib.lib().lgpu_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    alg = None
+    if rank == 0:
+        import ctypes
+        L = _lib.lib()
+        nk = 9
+        msa = (ctypes.c_double * nk)(); by = (ctypes.c_double * nk)(); sc = (ctypes.c_ulonglong * nk)(); kn = (ctypes.c_ulonglong * nk)()
+        L.lgpu_profile_enable(1)
+        rep.run()
+        torch.cuda.synchronize()
+        L.lgpu_profile_enable(0)
+        L.lgpu_profile_read(msa, by, sc, kn)
+        names = ["ntt_fwd", "ntt_inv", "vecop", "modup", "mac", "tensor", "automorphism", "fused", "epilogue"]
+        alg = {"sum_alg_GB_per_step": sum(by) / 1e9, "classes": {names[i]: {"ms": msa[i], "alg_GB": by[i] / 1e9, "kernels": int(kn[i])} for i in range(nk) if sc[i]}}
+    barrier()
+    if rank == 0:
+        line = {"metric": "CKKS bootstraps/s (op-trace replay of circuits/ckks/bootstrapping, N16QP1767H32768H32 shapes)", "value": args.batch * world * args.steps / t_max,
+                "unit": "bootstraps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "ckks_bootstrap_replay", "preset": args.preset, "logN": s["logN"], "q_limbs": len(s["Q"]), "p_limbs": len(s["P"]),
+                           "batch_per_gpu": args.batch, "global_batch": args.batch * world, "ops_per_bootstrap": len(trace), "galois_keys": rep.n_galois_keys,
+                           "trace": boottrace.summarize(trace),
+                           "l2_policy": "working set (keys, diagonals, batch) far exceeds L2; no flush", "timing": "CUDA events, max over ranks"},
+                "clocks": clocks, "gpu_launches": int(launches), "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+                "algorithmic_bytes": alg, "e2e": None, "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
+    if args.workload == "bootstrap":
+        return bootstrap_main(args)
     if args.impl == "reference":
         return reference_main(args)
     return gpu_main(args)

@@ -177,6 +177,13 @@ int lgpu_map_small_dimension_to_larger_dimension_ntt(lgpu_ctx* ctx, const uint64
 int lgpu_extend_basis_small_norm_and_center(lgpu_ctx* ctx, const uint64_t* poly_in_q, int level_p, uint64_t* poly_out_p,
                                             int batch, size_t stride_q, size_t stride_p, void* stream);
 
+/* bootstrapping.Evaluator.ModUp's coefficient loops (circuits/ckks/bootstrapping/evaluator.go:652-699, :729-741): the value of row 0 (mod q_0,
+ * coefficient domain) centred around q_0 and written modulo q_i on rows first_q..level_q of out_q and modulo p_j on rows 0..level_p of out_p
+ * (level_p = -1: none). strict = 0 uses the reference's `coeff >= q/2` test (ctIn.Value[0], and Value[1] without ephemeral key), strict = 1
+ * its `coeff > q/2` (Value[1] on the sparse-key path). Literal: a negative multiple of a modulus is written as that modulus. */
+int lgpu_modup_centered(lgpu_ctx* ctx, const uint64_t* row0, int first_q, int level_q, int level_p, int strict, uint64_t* out_q,
+                        uint64_t* out_p, int batch, size_t stride_in, size_t stride_q, size_t stride_p, void* stream);
+
 /* ---- RNS basis extension (ring/basis_extension.go) -------------------------------------------------------
  * polQ has levelQ+1 rows, polP has levelP+1 rows; `batch` polynomials with the given strides (words). */
 /* BasisExtender.ModUpQtoP (:177-190) / ModUpPtoQ (:195-209): outputs are the reference's exact (non-canonical,

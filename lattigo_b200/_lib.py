@@ -61,6 +61,7 @@ def lib():
             "lgpu_mult_by_monomial": [vp, i, i, vp, i, vp, i, z, vp],
             "lgpu_map_small_dimension_to_larger_dimension_ntt": [vp, vp, i, vp, i, i, vp],
             "lgpu_extend_basis_small_norm_and_center": [vp, vp, i, vp, i, z, z, vp],
+            "lgpu_modup_centered": [vp, vp, i, i, i, i, vp, vp, i, z, z, z, vp],
             "lgpu_modup_qtop": [vp, i, i, vp, vp, i, z, z, vp],
             "lgpu_modup_ptoq": [vp, i, i, vp, vp, i, z, z, vp],
             "lgpu_moddown_qp_to_q": [vp, i, i, vp, vp, vp, i, z, z, vp],

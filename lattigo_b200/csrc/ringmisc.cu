@@ -111,6 +111,32 @@ static int move_common(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, u
     return 0;
 }
 
+// bootstrapping.Evaluator.ModUp's coefficient loops (circuits/ckks/bootstrapping/evaluator.go:652-699, :729-741): row 0 (mod q_0) is lifted,
+// centred around q_0, to the Q rows [first_q, level_q] and the P rows [0, level_p] of the output, literally:
+//   coeff >= q/2 (strict = 0) or coeff > q/2 (strict = 1)  ->  coeff = q - coeff, negative;   out = BRedAdd(coeff) or Q_i - BRedAdd(coeff)
+// (a negative multiple of Q_i therefore comes out as Q_i, not 0, like in the reference).
+__global__ void __launch_bounds__(256) modup_centered_kernel(const u64* in, u64* out_q, u64* out_p, const lgpu::LimbConst* limbs, int nQ, int first_q,
+                                                             int nq, int np, int n, int strict, size_t in_bs, size_t q_bs, size_t p_bs) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int b = blockIdx.z;
+    const u64 q = limbs[0].q;
+    u64 coeff = in[(size_t)b * in_bs + j];
+    const bool neg = strict ? (coeff > (q >> 1)) : (coeff >= (q >> 1));
+    if (neg) coeff = q - coeff;
+    for (int i = first_q; i < nq; i++) {
+        const lgpu::LimbConst& L = limbs[i];
+        const u64 t = lgpu::bred_add(coeff, L.q, L.bred_hi);
+        out_q[(size_t)b * q_bs + (size_t)i * n + j] = neg ? L.q - t : t;
+    }
+    for (int i = 0; i < np; i++) {
+        const lgpu::LimbConst& L = limbs[nQ + i];
+        const u64 t = lgpu::bred_add(coeff, L.q, L.bred_hi);
+        out_p[(size_t)b * p_bs + (size_t)i * n + j] = neg ? L.q - t : t;
+    }
+}
+
+
 extern "C" {
 
 int lgpu_shift(lgpu_ctx* ctx, int ring, int level, const uint64_t* in, int k, uint64_t* out, int batch, size_t batch_stride, void* stream) {
@@ -152,6 +178,19 @@ int lgpu_extend_basis_small_norm_and_center(lgpu_ctx* ctx, const uint64_t* poly_
     const Ctx& c = ctx->c;
     extend_small_norm_kernel<<<dim3((unsigned)((c.N + 255) / 256), 1, batch), 256, 0, (cudaStream_t)stream>>>(
         (const u64*)poly_in_q, (u64*)poly_out_p, c.d_limbs, c.nQ, level_p + 1, c.N, stride_q, stride_p);
+    LGPU_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int lgpu_modup_centered(lgpu_ctx* ctx, const uint64_t* row0, int first_q, int level_q, int level_p, int strict, uint64_t* out_q, uint64_t* out_p,
+                        int batch, size_t stride_in, size_t stride_q, size_t stride_p, void* stream) {
+    REQUIRE_DEVICE(ctx);
+    REQUIRE(row0 && (out_q || level_q < first_q) && (out_p || level_p < 0), "null polynomial");
+    const Ctx& c = ctx->c;
+    REQUIRE(first_q >= 0 && level_q < c.nQ && level_p < c.nP, "level out of range");
+    REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
+    modup_centered_kernel<<<dim3((unsigned)((c.N + 255) / 256), 1, batch), 256, 0, (cudaStream_t)stream>>>(
+        (const u64*)row0, (u64*)out_q, (u64*)out_p, c.d_limbs, c.nQ, first_q, level_q + 1, level_p + 1, c.N, strict, stride_in, stride_q, stride_p);
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
 }
