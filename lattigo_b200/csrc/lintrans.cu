@@ -93,12 +93,69 @@ __global__ void __launch_bounds__(256) lt_perm_mac_kernel(LtPermMacParams p) {
     const u64 q = L.q, qinv = L.qinv;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= p.n) return;
-    const size_t src = (size_t)__ldg(p.index + j);
+    const size_t src = p.index ? (size_t)__ldg(p.index + j) : (size_t)j;
     const u64 e = (isP ? p.ptP : p.ptQ)[(size_t)jr * p.n + j];
     const size_t so = (size_t)blockIdx.z * p.src_bs + (size_t)r * p.n, oo = (size_t)blockIdx.z * p.out_bs + (size_t)r * p.n;
     u64 v0 = mred(e, p.src0[so + src], q, qinv), v1 = mred(e, p.src1[so + src], q, qinv);
     if (!p.first) { v0 = cred(v0 + p.out0[oo + j], q); v1 = cred(v1 + p.out1[oo + j], q); }
     p.out0[oo + j] = v0; p.out1[oo + j] = v1;
+}
+
+// AutomorphismHoistedLazy in ONE pass (core/rlwe/evaluator_automorphism.go:107-165 = gadgetProductMultiplePLazyHoisted :401-453 + the P * ct0 term +
+// AutomorphismNTTWithIndex on the four polynomials): the thread of OUTPUT coefficient j evaluates the whole digit sum at source position
+// index[j]. In the bit-reversed NTT layout an automorphism maps every aligned block of 2^k coefficients onto an aligned block (multiplication by
+// an odd Galois element preserves the low bits that select the block), so a warp's 32 gathered 8-byte reads cover exactly one 256-byte block:
+// the gather costs no extra sectors, and the separate MAC passes (accumulators re-read and re-written per digit) and permutation passes go away.
+// index == nullptr: no permutation (the plain hoisted product).
+struct HoistParams {
+    const LimbConst* limbs;
+    const u64* decomp; size_t d_ds, d_bs; int d_pshift;   // [digit][batch][nqd + np][N]; P rows start d_pshift rows after row nq
+    const u64* evk; size_t e_ds, e_cs; int nQk;          // digit stride, component stride; the key's P rows start at row nQk
+    const u64* ct0P; size_t c_bs;                        // P * ct0 on the Q rows (nullptr: none)
+    u64* out0; u64* out1; size_t o_bs;                   // QP-stacked [batch][nq + np][N]
+    const u64* index;
+    int nq, np, nQfull, nd, n, batch;
+};
+constexpr int kHoistB = 4;   // batch elements per thread: the key words are loaded once for all of them
+__global__ void __launch_bounds__(256) lt_hoisted_auto_kernel(HoistParams p) {
+    const int r = blockIdx.y;
+    const bool isP = r >= p.nq;
+    const int jr = isP ? r - p.nq : r;
+    const LimbConst L = p.limbs[isP ? p.nQfull + jr : jr];
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.n) return;
+    const size_t src = p.index ? (size_t)__ldg(p.index + j) : (size_t)j;
+    const size_t drow = (size_t)(isP ? r + p.d_pshift : r) * p.n + src;
+    const size_t erow = (size_t)(isP ? p.nQk + jr : jr) * p.n + src;
+    for (int b0 = blockIdx.z * kHoistB; b0 < p.batch; b0 += gridDim.z * kHoistB) {
+        u64 a0[kHoistB], a1[kHoistB];
+#pragma unroll
+        for (int t = 0; t < kHoistB; t++) { a0[t] = 0; a1[t] = 0; }
+        for (int d = 0; d < p.nd; d++) {
+            const u64 e0 = __ldg(p.evk + (size_t)d * p.e_ds + erow), e1 = __ldg(p.evk + (size_t)d * p.e_ds + p.e_cs + erow);
+            const u64* x = p.decomp + (size_t)d * p.d_ds + drow;
+#pragma unroll
+            for (int t = 0; t < kHoistB; t++) {
+                if (b0 + t < p.batch) {
+                    const u64 xv = x[(size_t)(b0 + t) * p.d_bs];
+                    u64 v0 = a0[t] + mred_lazy(e0, xv, q, qinv), v1 = a1[t] + mred_lazy(e1, xv, q, qinv);
+                    a0[t] = v0 >= twoq ? v0 - twoq : v0;
+                    a1[t] = v1 >= twoq ? v1 - twoq : v1;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kHoistB; t++) {
+            if (b0 + t < p.batch) {
+                u64 v0 = cred(a0[t], q);
+                if (p.ct0P && !isP) v0 = cred(v0 + p.ct0P[(size_t)(b0 + t) * p.c_bs + (size_t)r * p.n + src], q);
+                const size_t o = (size_t)(b0 + t) * p.o_bs + (size_t)r * p.n + j;
+                p.out0[o] = v0;
+                p.out1[o] = cred(a1[t], q);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -141,11 +198,41 @@ static std::vector<u64> p_mod_q_mont(const Ctx* c, int levelQ, int levelP) {
 
 // Evaluator.AutomorphismHoistedLazy (core/rlwe/evaluator_automorphism.go:107-165), NTT-domain branch: out = pi_galEl(
 // <decomp, gk> + (P * ct0, 0)) mod QP. ct0P = P * ct0 (rows [0, levelQ], canonical).
+static int check_gk(const Ctx* c, int levelQ, const GadgetCt& gk) {
+    if (!gk.data || gk.levelQ < levelQ || gk.levelQ >= c->nQ || gk.levelP < 0 || gk.levelP >= c->nP) { set_error("Galois key levels out of range"); return -1; }
+    if (gk.pw2 != 0) { set_error("method is unsupported for BaseTwoDecomposition != 0"); return -1; }
+    if (gk.ndigits < base_rns_decomposition_vector_size(levelQ, gk.levelP)) { set_error("Galois key has too few digits"); return -1; }
+    return 0;
+}
+
 int automorphism_hoisted_lazy(const Ctx* c, int levelQ, CSpan ct0P, const u64* decomp, int decomp_levelQ, u64 galEl, const GadgetCt& gk,
                               const AccSpans& out, int batch, cudaStream_t st) {
     const int levelP = gk.levelP;
     if (levelP < 0) { set_error("AutomorphismHoistedLazy requires a P ring"); return -1; }
-    const size_t N = c->N, nq = levelQ + 1, np = levelP + 1;
+    if (check_gk(c, levelQ, gk)) return -1;
+    if (decomp_levelQ < 0) decomp_levelQ = levelQ;
+    const size_t N = c->N, nq = levelQ + 1, np = levelP + 1, nqd = decomp_levelQ + 1;
+    const bool stacked = out.q[0].row_stride == N && out.p[0].p == out.q[0].p + nq * N && out.p[1].p == out.q[1].p + nq * N &&
+                         out.q[0].batch_stride == out.q[1].batch_stride && out.p[0].batch_stride == out.q[0].batch_stride &&
+                         out.p[1].batch_stride == out.q[0].batch_stride && out.p[0].row_stride == N && ct0P.row_stride == N;
+    if (stacked) {
+        Scratch ib;
+        if (ib.alloc(N, st)) return -1;
+        if (automorphism_ntt_index(c, galEl, ib.p, st)) return -1;
+        HoistParams p;
+        p.limbs = c->d_limbs; p.decomp = decomp; p.d_ds = (size_t)batch * (nqd + np) * N; p.d_bs = (nqd + np) * N; p.d_pshift = (int)(nqd - nq);
+        const size_t key_rows = (size_t)(gk.levelQ + 1) + (size_t)(gk.levelP + 1);
+        p.evk = gk.data; p.e_cs = key_rows * N; p.e_ds = (size_t)gk.npw2max * 2 * key_rows * N; p.nQk = gk.levelQ + 1;
+        p.ct0P = ct0P.p; p.c_bs = ct0P.batch_stride;
+        p.out0 = out.q[0].p; p.out1 = out.q[1].p; p.o_bs = out.q[0].batch_stride;
+        p.index = ib.p; p.nq = (int)nq; p.np = (int)np; p.nQfull = c->nQ; p.nd = base_rns_decomposition_vector_size(levelQ, levelP); p.n = c->N; p.batch = batch;
+        // decomposition once, key once per group of kHoistB ciphertexts, P * ct0 on the Q rows, two outputs
+        ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * ((double)(nq + np) * (p.nd * (batch + 2.0 * ((batch + kHoistB - 1) / kHoistB)) + 2.0 * batch) + (double)nq * batch), 1);
+        const int zb = std::max(1, std::min(16, (batch + kHoistB - 1) / kHoistB));
+        lt_hoisted_auto_kernel<<<dim3((c->N + 255) / 256, (unsigned)(nq + np), zb), 256, 0, st>>>(p);
+        LGPU_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     Scratch buf;
     if (buf.alloc((size_t)2 * batch * (nq + np) * N + N, st)) return -1;
     AccSpans acc = stacked_acc(buf.p, nq, np, N, batch);
@@ -258,16 +345,14 @@ static int multiply_naive(const LtState& s, const LinTransView& m, int levelQ, u
         const GadgetCt* gk = s.gks->find(galEl);
         if (!gk) return -1;
         if (gk->levelP != s.levelP) { set_error("LinearTransformation.LevelP != GaloisKey.LevelP()"); return -1; }
-        if (gadget_product_hoisted_lazy(c, levelQ, s.decomp, *gk, acc, s.batch, s.st, s.levelQd)) return -1;
-        if (launch_vecop(c, rows_range(0, 0, (int)nq), LGPU_OP_ADD, CSpan{acc.q[0].p, N, (nq + np) * N}, CSpan{s.ctP, N, s.nqd * N}, acc.q[0], s.batch,
-                         nullptr, nullptr, 0, 0, c->N, s.st)) return -1;
-        if (automorphism_ntt_index(c, galEl, index, s.st)) return -1;
+        // rotated hoisted product in one pass (the permutation is folded into it), then the diagonal multiply-accumulate without gather
+        if (automorphism_hoisted_lazy(c, levelQ, CSpan{s.ctP, N, s.nqd * N}, s.decomp, s.levelQd, galEl, *gk, acc, s.batch, s.st)) return -1;
         const u64* pt = diag_of(m, keys[i]);
         LtPermMacParams p;
         p.limbs = c->d_limbs; p.ptQ = pt; p.ptP = pt + (size_t)(m.level_q + 1) * N;
         p.src0 = ab; p.src1 = ab + per / 2; p.src_bs = (nq + np) * N;
         p.out0 = cb; p.out1 = cb + per / 2; p.out_bs = (nq + np) * N;
-        p.index = index; p.first = (i == 0); p.nq = (int)nq; p.np = (int)np; p.nQfull = c->nQ; p.n = c->N;
+        p.index = nullptr; p.first = (i == 0); p.nq = (int)nq; p.np = (int)np; p.nQfull = c->nQ; p.n = c->N;
         ProfScope ps(LGPU_KCLASS_MAC, s.st, 8.0 * N * (nq + np) * (1.0 + s.batch * (p.first ? 4.0 : 6.0)), 1);
         dim3 grid((c->N + 255) / 256, (unsigned)(nq + np), s.batch);
         lt_perm_mac_kernel<<<grid, 256, 0, s.st>>>(p);
@@ -339,7 +424,9 @@ static int multiply_bsgs(const LtState& s, const LinTransView& m, const PreRot& 
         if (j != 0) {
             // hoisted ModDown of the c1 part, key-switch to the giant-step rotation, rotate, accumulate (:409-436)
             u64* t1 = tb + per / 2;
-            if (moddown_qp_to_q_ntt(c, levelQ, s.levelP, CSpan{t1, N, sbs}, CSpan{t1 + nq * N, N, sbs}, Span{t1d, N, nq * N}, s.batch, s.st)) return -1;
+            if (fz_applicable(c, levelQ, s.levelP)) {
+                if (moddown_ntt_fused(c, levelQ, s.levelP, t1, 0, sbs, nullptr, 0, 0, t1d, 0, nq * N, 1, s.batch, s.st)) return -1;
+            } else if (moddown_qp_to_q_ntt(c, levelQ, s.levelP, CSpan{t1, N, sbs}, CSpan{t1 + nq * N, N, sbs}, Span{t1d, N, nq * N}, s.batch, s.st)) return -1;
             const u64 galEl = galois_element(c, j);
             const GadgetCt* gk = s.gks->find(galEl);
             if (!gk) return -1;

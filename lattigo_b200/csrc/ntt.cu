@@ -339,13 +339,9 @@ int launch_ntt_mul_montgomery(const Ctx* c, const RowMap& rm, CSpan in, CSpan ot
             ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 24.0 * c->N * fp.nrows * batch, 1);
             if (launch_ntt_persist(c, fp, false, 0, in, out, batch, st, other)) return -1;
         }
-        // integer rows: group by correction kind like launch_ntt_int does (fast_variant is per launch)
+        // integer rows: their transform is bound by the integer pipes, which the product would share -- measured 0.9x against two launches
+        // (profiles/r02_configs.json, C2 q61), so they keep the transform followed by the coefficient-wise kernel
         if (rest.nrows > 0) {
-            const int fast = fast_variant(c, rest, false);
-            if (fast != 0) {
-                ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 24.0 * c->N * rest.nrows * batch, 1);
-                return launch_ntt_persist(c, rest, false, fast, in, out, batch, st, other);
-            }
             if (launch_ntt_int(c, rest, in, out, batch, NTT_CANONICAL, st)) return -1;
             return launch_vecop(c, rest, LGPU_OP_MULCOEFFSMONTGOMERY, CSpan{out.p, out.row_stride, out.batch_stride}, other, out, batch, nullptr, nullptr, 0, 0,
                                 c->N, st);

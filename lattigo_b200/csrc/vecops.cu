@@ -83,9 +83,10 @@ __global__ void __launch_bounds__(256) vecop_kernel(VecParams p) {
     const int row = blockIdx.y, b = blockIdx.z;
     const LimbConst L = p.limbs[p.rm.limb[row]];
     const u64 s0 = p.s0[row], s1 = p.s1[row];
-    const u64* p1 = op_uses_p1(OP) ? p.p1 + (size_t)b * p.bs1 + (size_t)row * p.rs1 : nullptr;
-    const u64* p2 = op_uses_p2(OP) ? p.p2 + (size_t)b * p.bs2 + (size_t)row * p.rs2 : nullptr;
-    u64* p3 = p.p3 + (size_t)b * p.bs3 + (size_t)row * p.rs3;
+    const size_t drow = p.rm.drow[row];        // data row of this launch row (identity for whole polynomials, sparse for row subsets)
+    const u64* p1 = op_uses_p1(OP) ? p.p1 + (size_t)b * p.bs1 + drow * p.rs1 : nullptr;
+    const u64* p2 = op_uses_p2(OP) ? p.p2 + (size_t)b * p.bs2 + drow * p.rs2 : nullptr;
+    u64* p3 = p.p3 + (size_t)b * p.bs3 + drow * p.rs3;
     const int nv = p.n / VEC;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) {
         if (VEC == 2) {
