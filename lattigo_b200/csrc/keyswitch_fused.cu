@@ -739,6 +739,104 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K3 for the integer rows (primes above 2^46: q0, the 56 / 60-bit levels of the bootstrapping chains, the 61-bit special primes), same
+// structure as ks_chunk_mac_fp8r_kernel: 512 threads x 8 coefficients, swizzled tile, pair / warp level exchanges, the last radix-8 round
+// and the MAC in registers, split mbarrier between digits. The 256 x 16 kernel it replaces (ks_chunk_mac_kernel<false>, kept as
+// LGPU_K3_INT_VARIANT=0) ran 16 warps per SM with CTA-wide barriers and cost 3.3x an FP64 row per row (profiles/r02_configs.json).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 2) ks_chunk_mac_int8r_kernel(KsChunkParams p) {
+    constexpr int CL = 12, T = 512;
+    extern __shared__ u64 smem[];
+    __shared__ __align__(8) u64 s_bar;
+    u64* sm = smem;
+    ulonglong2* accs = reinterpret_cast<ulonglong2*>(smem + 4096);
+    const int b = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+    const int limb = p.rm.limb[blockIdx.z];
+    const int row = p.rm.drow[blockIdx.z];
+    const LimbConst L = p.limbs[limb];
+    const int s1 = p.logN - CL;
+    const int N = 1 << p.logN;
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1, nq = 0ull - q, kq = L.kq;
+    const unsigned mask = L.fwd_mask;
+    const ulonglong2* tw = L.tw_fwd;
+    const size_t erow = (size_t)(row < p.nq ? row : p.nQk + (row - p.nq)) * N + ((size_t)chunk << CL);
+    const u64* P1row = p.P1 + (size_t)b * p.p1_bs + (size_t)row * N + ((size_t)chunk << CL);
+    const u64* xin = p.cx + (size_t)b * p.cx_bs + (size_t)row * p.cx_rs + ((size_t)chunk << CL) + 8 * tid;
+    const int own_d = row < p.nq ? row / p.k : -1;
+    const unsigned bar = smem_addr(&s_bar);
+    if (tid == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(T) : "memory");
+    __syncthreads();
+    u64 tok = 0;
+    bool pending = false;
+    for (int d = 0; d < p.nd; d++) {
+        const bool own = d == own_d;
+        const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow + 8 * tid;
+        const u64* e1 = e0 + p.evk_cs;
+        int dn = d + 1;
+        if (dn == own_d) dn++;
+        u64 xv[8];
+        if (!own) {
+            {
+                u64 x[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) x[k] = P1row[(size_t)d * p.p1_ds + k * T + tid];
+                if (KS_L2_PREFETCH && dn < p.nd && tid < 256)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P1row + (size_t)dn * p.p1_ds + tid * 16));
+                int8_bflys<0>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
+                if (pending) { mbar_wait(bar, tok); pending = false; }
+                i8s_store_r1(sm, x, tid);
+            }
+            __syncthreads();
+            i8s_round2(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+            fp8s_pair_sync(tid);
+            i8s_round3(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+            __syncwarp();
+            i8s_load_r4(sm, xv, tid);
+            tok = mbar_arrive(bar);
+            pending = true;
+            int8_bflys<9>(xv, tw, s1, chunk, tid, nq, twoq, kq, mask);     // lazy values below 2 kq: any u64 is a valid MRedLazy operand
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const ulonglong2 v = ldg128(xin + 2 * j); xv[2 * j] = v.x; xv[2 * j + 1] = v.y; }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            ulonglong2 k0[2], k1[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) { k0[j] = ldg128(e0 + 4 * h + 2 * j); k1[j] = ldg128(e1 + 4 * h + 2 * j); }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int pj = 2 * h + j;
+                const u64 xa = xv[2 * pj], xb = xv[2 * pj + 1];
+                ulonglong2 m0, m1;
+                m0.x = mred_lazy(k0[j].x, xa, q, qinv); m0.y = mred_lazy(k0[j].y, xb, q, qinv);
+                m1.x = mred_lazy(k1[j].x, xa, q, qinv); m1.y = mred_lazy(k1[j].y, xb, q, qinv);
+                ulonglong2* A0 = accs + (size_t)(0 * 4 + pj) * T + tid;
+                ulonglong2* A1 = accs + (size_t)(1 * 4 + pj) * T + tid;
+                if (d != 0) {
+                    // terms are below 2q and q reaches 2^61: keep the running sums below 2q (4q fits 64 bits)
+                    const ulonglong2 c0 = *A0, c1 = *A1;
+                    m0.x += c0.x; m0.y += c0.y; m1.x += c1.x; m1.y += c1.y;
+                    m0.x = m0.x >= twoq ? m0.x - twoq : m0.x; m0.y = m0.y >= twoq ? m0.y - twoq : m0.y;
+                    m1.x = m1.x >= twoq ? m1.x - twoq : m1.x; m1.y = m1.y >= twoq ? m1.y - twoq : m1.y;
+                }
+                *A0 = m0; *A1 = m1;
+            }
+        }
+    }
+    u64* o0 = p.acc + (size_t)b * p.acc_bs + (size_t)row * N + ((size_t)chunk << CL) + 8 * tid;
+    u64* o1 = o0 + p.acc_cs;
+#pragma unroll
+    for (int pj = 0; pj < 4; pj++) {
+        const ulonglong2 c0 = accs[(size_t)(0 * 4 + pj) * T + tid], c1 = accs[(size_t)(1 * 4 + pj) * T + tid];
+        ulonglong2 r0, r1;
+        r0.x = cred(c0.x, q); r0.y = cred(c0.y, q); r1.x = cred(c1.x, q); r1.y = cred(c1.y, q);
+        *reinterpret_cast<ulonglong2*>(o0 + 2 * pj) = r0;
+        *reinterpret_cast<ulonglong2*>(o1 + 2 * pj) = r1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------------------
 bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
@@ -875,8 +973,15 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
             if (ks_launch_strided<false>(s1, nsmax, sp, dim3(gx, in.nrows, nd * batch), sint)) return -1;
         }
         ProfScope ps(LGPU_KCLASS_MAC, sint, 8.0 * N * in.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
-        LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ks_chunk_mac_kernel<false><<<dim3(batch, chunks, in.nrows), 256, smem, sint>>>(cp);
+        // LGPU_K3_INT_VARIANT=0 selects the 256 x 16 shared-memory-MAC kernel (cross-check of the default 512 x 8 register-MAC one)
+        static const int k3i = [] { const char* e = getenv("LGPU_K3_INT_VARIANT"); return e ? atoi(e) : 8; }();
+        if (k3i != 0) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_int8r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_int8r_kernel<<<dim3(batch, chunks, in.nrows), 512, smem, sint>>>(cp);
+        } else {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_kernel<false><<<dim3(batch, chunks, in.nrows), 256, smem, sint>>>(cp);
+        }
         LGPU_CUDA_OK(cudaGetLastError());
     }
     if (fp.nrows) {
@@ -1058,6 +1163,61 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
     }
 }
 
+// integer-row variant of fz_chunk_epi_fp8_kernel (512 threads x 8 elements, last round and epilogue in registers)
+__global__ void __launch_bounds__(512, 2) fz_chunk_epi_int8_kernel(FzChunkParams p) {
+    constexpr int CL = 12, T = 512;
+    extern __shared__ u64 smem[];
+    u64* sm = smem;
+    const int chunk = blockIdx.x, z = blockIdx.z, tid = threadIdx.x;
+    const int limb = p.rm.limb[blockIdx.y];
+    const int row = p.rm.drow[blockIdx.y];
+    const LimbConst L = p.limbs[limb];
+    const int s1 = p.logN - CL;
+    const int N = 1 << p.logN;
+    const u64 q = L.q, qinv = L.qinv, twoq = q << 1, nq = 0ull - q, kq = L.kq;
+    const unsigned mask = L.fwd_mask;
+    const ulonglong2* tw = L.tw_fwd;
+    const u64 sc = p.s[blockIdx.y];
+    const int zc = z / p.nb, zb = z % p.nb;
+    const size_t roff = (size_t)row * N + ((size_t)chunk << CL);
+    const u64* src = p.P1 + (size_t)z * p.p1_bs + roff;
+    const u64* A = p.A + (size_t)zc * p.a_cs + (size_t)zb * p.a_bs + roff;
+    const u64* D = p.D ? p.D + (size_t)zc * p.d_cs + (size_t)zb * p.d_bs + roff : nullptr;
+    u64* out = p.out + (size_t)zc * p.o_cs + (size_t)zb * p.o_bs + roff;
+    {
+        u64 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = src[k * T + tid];
+        int8_bflys<0>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
+        i8s_store_r1(sm, x, tid);
+    }
+    __syncthreads();
+    i8s_round2(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+    fp8s_pair_sync(tid);
+    i8s_round3(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+    ulonglong2 a[4], d[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        a[j] = *reinterpret_cast<const ulonglong2*>(A + 8 * tid + 2 * j);
+        d[j] = D ? *reinterpret_cast<const ulonglong2*>(D + 8 * tid + 2 * j) : make_ulonglong2(0, 0);
+    }
+    __syncwarp();
+    u64 x[8];
+    i8s_load_r4(sm, x, tid);
+    int8_bflys<9>(x, tw, s1, chunk, tid, nq, twoq, kq, mask);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        // lazy transform output below 2 kq (up to ~2^64 for 60 / 61-bit primes): one correction keeps x + 2q - a inside 64 bits
+        u64 xa = x[2 * j], xb = x[2 * j + 1];
+        xa = xa >= kq ? xa - kq : xa; xb = xb >= kq ? xb - kq : xb;
+        ulonglong2 r;
+        r.x = mred(xa + twoq - a[j].x, sc, q, qinv);
+        r.y = mred(xb + twoq - a[j].y, sc, q, qinv);
+        if (D) { r.x = cred(r.x + d[j].x, q); r.y = cred(r.y + d[j].y, q); }
+        *reinterpret_cast<ulonglong2*>(out + 8 * tid + 2 * j) = r;
+    }
+}
+
 template <bool FP>
 static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
     const size_t smem = (size_t)(4096 + 256 + 8) * sizeof(u64);
@@ -1066,6 +1226,11 @@ static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
                         even_words(p.o_cs, p.o_bs);
     if (FP && v8 == 8 && vec_ok) {
         fz_chunk_epi_fp8_kernel<<<grid, 512, smem, st>>>(p);
+        LGPU_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    if (!FP && v8 == 8 && vec_ok) {
+        fz_chunk_epi_int8_kernel<<<grid, 512, smem, st>>>(p);
         LGPU_CUDA_OK(cudaGetLastError());
         return 0;
     }

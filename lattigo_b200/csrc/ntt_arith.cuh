@@ -501,4 +501,56 @@ __device__ __forceinline__ void fp8s_load_r4(const double* fsm, double (&x)[8], 
     for (int k = 0; k < 8; k++) x[k] = fsm[tb ^ k];
 }
 
+
+// ---- the same four radix-8 rounds for the integer (Shoup) butterflies: 512 threads x 8 elements on the XOR-swizzled u64 tile. Twiddle pairs are
+// read where they are used (16 bytes each, L1-resident; rounds 1-2 are warp-uniform) instead of being held in 28 registers. `mask` is the
+// prime's lazy-correction schedule (LimbConst.fwd_mask: 0 below 2^57, every other stage for 60-bit primes, every stage for 61-bit ones).
+template <int A>
+__device__ __forceinline__ void int8_bflys(u64 (&x)[8], const ulonglong2* tw, int s1, int chunk, int hi, u64 nq, u64 twoq, u64 kq, unsigned mask) {
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+        const int half = 4 >> u;
+        const int twbase = (1 << (s1 + A + u)) + (chunk << (A + u)) + (hi << u);
+        const bool corr = (mask >> (s1 + A + u)) & 1u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k & half) continue;
+            fast_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), nq, twoq, kq, corr);
+        }
+    }
+}
+__device__ __forceinline__ void i8s_store_r1(u64* sm, const u64 (&x)[8], int tid) {
+    u64* a = sm + swz(tid);
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[512 * k] = x[k];
+}
+__device__ __forceinline__ void i8s_round2(u64* sm, const ulonglong2* tw, int s1, int chunk, int tid, u64 nq, u64 twoq, u64 kq, unsigned mask) {
+    const int tb = swz(((tid >> 6) << 9) + (tid & 63));
+    u64* a0 = sm + tb;
+    u64* a1 = sm + (tb ^ 9);
+    u64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = ((k & 1) ? a1 : a0)[64 * k];
+    int8_bflys<3>(x, tw, s1, chunk, tid >> 6, nq, twoq, kq, mask);
+#pragma unroll
+    for (int k = 0; k < 8; k++) ((k & 1) ? a1 : a0)[64 * k] = x[k];
+}
+__device__ __forceinline__ void i8s_round3(u64* sm, const ulonglong2* tw, int s1, int chunk, int tid, u64 nq, u64 twoq, u64 kq, unsigned mask) {
+    const int tb = swz(((tid >> 3) << 6) + (tid & 7));
+    u64* a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = sm + ((tb ^ ((k & 1) << 3) ^ ((k >> 1) << 1)) + ((k >> 1) << 4));
+    u64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = *a[k];
+    int8_bflys<6>(x, tw, s1, chunk, tid >> 3, nq, twoq, kq, mask);
+#pragma unroll
+    for (int k = 0; k < 8; k++) *a[k] = x[k];
+}
+__device__ __forceinline__ void i8s_load_r4(const u64* sm, u64 (&x)[8], int tid) {
+    const int tb = swz(tid << 3);
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = sm[tb ^ k];
+}
+
 }  // namespace lgpu

@@ -465,6 +465,93 @@ struct IntFwdOps {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// forward, integer primes, second generation: the tile code of FpFwdOps2 with Shoup butterflies (512 threads x 8 elements, swizzled tile,
+// one CTA barrier, pair / warp exchanges, coalesced copy-out of canonical residues). The 256 x 16 IntFwdOps ran 16 warps per SM at 128
+// registers; this one runs 32 at 64. The per-prime correction schedule is evaluated at run time (all-zero below 2^57).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int RL>
+struct IntFwdOps2 {
+    static constexpr int T = 512, MINB = 2;
+    static constexpr bool kInverse = false;
+    static constexpr size_t kSmem = (size_t)4096 * sizeof(u64);
+    static constexpr int kN1 = 4096 / T;
+    static constexpr int kN2 = 1 << RL;
+
+    static __device__ __forceinline__ void pass1(const PersistParams& p, int lt, int j, u64*) {
+        constexpr int R = 1 << RL, stride = 4096;
+        const TileRef t = tile_ref(p, lt);
+        const LimbConst& L = p.limbs[t.limb];
+        const int l = j * T + threadIdx.x;
+        const u64 q = L.q;
+        const ulonglong2* tw = L.tw_fwd;
+        const u64 nq = 0ull - q, twoq = q << 1, kq = L.kq;
+        const unsigned mask = L.fwd_mask;
+        u64 x[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) x[k] = t.in[(size_t)k * stride + l];
+#pragma unroll
+        for (int u = 0; u < RL; u++) {
+            const int half = 1 << (RL - 1 - u);
+            const bool corr = (mask >> u) & 1u;
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (k & half) continue;
+                fast_fwd_bfly(x[k], x[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), nq, twoq, kq, corr);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) t.out[(size_t)k * stride + l] = x[k];
+    }
+
+    static __device__ __forceinline__ void pass2(const PersistParams& p, int lt, int chunk, u64* sm) {
+        constexpr int s1 = RL;
+        const int tid = threadIdx.x;
+        const TileRef t = tile_ref(p, lt);
+        const LimbConst& L = p.limbs[t.limb];
+        u64* io = t.out + ((size_t)chunk << 12);
+        const u64 q = L.q, nq = 0ull - q, twoq = q << 1, kq = L.kq, bhi = L.bred_hi;
+        const unsigned mask = L.fwd_mask;
+        const ulonglong2* tw = L.tw_fwd;
+        {
+            u64 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = __ldcg(io + k * T + tid);
+            int8_bflys<0>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
+            i8s_store_r1(sm, x, tid);
+        }
+        __syncthreads();
+        i8s_round2(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+        fp8s_pair_sync(tid);
+        i8s_round3(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+        __syncwarp();
+        {
+            const int tb = swz(tid << 3);
+            u64 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = sm[tb ^ k];
+            int8_bflys<9>(x, tw, s1, chunk, tid, nq, twoq, kq, mask);
+#pragma unroll
+            for (int k = 0; k < 8; k++) sm[tb ^ k] = bred_add(x[k], q, bhi);            // reducevec, ring/ntt.go:176
+        }
+        __syncwarp();
+        {
+            const int w0 = (tid >> 5) << 8, lane = tid & 31;
+            const int tb = swz(w0 + lane);
+            u64* g = io + w0 + lane;
+            if (t.mul) {
+                const u64* mu = t.mul + ((size_t)chunk << 12) + w0 + lane;
+                const u64 qinv = L.qinv;
+#pragma unroll
+                for (int m = 0; m < 8; m++) g[32 * m] = mred(sm[(tb ^ ((m & 1) << 2) ^ (((m >> 1) & 1) * 9)) + 32 * m], __ldg(mu + 32 * m), q, qinv);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; m++) g[32 * m] = sm[(tb ^ ((m & 1) << 2) ^ (((m >> 1) & 1) * 9)) + 32 * m];
+            }
+        }
+    }
+};
+
 template <int RL, int FAST>
 struct IntInvOps {
     static constexpr int T = 256, MINB = 2;
@@ -823,6 +910,8 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
     // the claim-ahead loop, 3 (default) = swizzled tile + pair/warp syncs + claim-ahead loop, 4 = 3 + TMA bulk prefetch of the next chunk (measured
     // 5 % slower than 3: profiles/r02_ntt_ab.json)
     static const int pv = [] { const char* e = getenv("LGPU_NTT_PERSIST_V"); return e ? atoi(e) : 3; }();
+    // LGPU_NTT_PERSIST_IV: integer forward tile code, 3 (default) = 512 x 8 swizzled (IntFwdOps2), 2 = 256 x 16 padded (IntFwdOps)
+    static const int piv = [] { const char* e = getenv("LGPU_NTT_PERSIST_IV"); return e ? atoi(e) : 3; }();
 #define PERSIST_CASE(RLV)                                                                                               \
     case RLV:                                                                                                           \
         if (kind == 0) {                                                                                                \
@@ -833,6 +922,7 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
             if (pv == 2) return persist_launch<FpFwdOps<RLV, 0>, true>(c, rm, in, out, batch, st, mul);                      \
             return persist_launch<FpFwdOps<RLV, 0>>(c, rm, in, out, batch, st, mul);                                         \
         }                                                                                                               \
+        if (!inverse && piv >= 3) return persist_launch<IntFwdOps2<RLV>, true>(c, rm, in, out, batch, st, mul);              \
         if (pv >= 2) {                                                                                                  \
             if (kind == 1) return inverse ? persist_launch<IntInvOps<RLV, 1>, true>(c, rm, in, out, batch, st, mul)          \
                                           : persist_launch<IntFwdOps<RLV, 1>, true>(c, rm, in, out, batch, st, mul);         \

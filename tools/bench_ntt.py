@@ -23,6 +23,7 @@ VARIANTS = {
     "persist_v3": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "3"},    # + swizzled tile, pair / warp level exchanges, hoisted addresses
     "persist_v4": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "4"},    # + TMA bulk prefetch of the next chunk into a double-buffered tile (default)
     "persist_ph1int": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PH1INT": "1"},   # strided stages on the integer pipes (v1 tile code)
+    "int_256x16": {"LGPU_NTT_PERSIST_IV": "2"},                            # integer rows: 256 x 16 padded tile (IntFwdOps) instead of the default 512 x 8 swizzled one
 }
 
 
