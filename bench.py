@@ -164,6 +164,33 @@ def _config(args, P, world):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(gpu_index):
+    """Pins this process (and therefore the pinned host buffers it first-touches afterwards) to the CPUs of the NUMA node the GPU hangs off:
+    the e2e path moves 8.8 GB per step over PCIe, and host memory on the far socket costs a third of the H2D bandwidth (round-1 SCALE run:
+    0.69 efficiency at 8 GPUs with unbound ranks). Returns a description for the JSON line; never fails the benchmark."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                             timeout=20).stdout.strip().lower()
+        if not bus:
+            return {"bound": False, "why": "no pci.bus_id"}
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]                                   # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {"bound": False, "why": "numa_node = -1 (single node or not reported)", "pci": bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus |= set(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"bound": False, "why": "no allowed CPU on node %d" % node, "pci": bus}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "numa_node": node, "cpus": len(allowed), "pci": bus}
+    except Exception as ex:  # noqa: BLE001
+        return {"bound": False, "why": repr(ex)[:120]}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -226,6 +253,7 @@ def gpu_main(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
 
     s = presets.PRESETS[args.preset]
     logN, Q, P = s["logN"], s["Q"], s["P"]
@@ -380,7 +408,8 @@ def gpu_main(args):
         e2e_ok = bool(torch.equal(ho.to(dev), out)) if out is not None else None
         e2e = {"value": B * world * e2e_steps / float(td.item()), "unit": UNIT, "h2d_bytes_per_step": int(2 * ha.numel() * 8),
                "d2h_bytes_per_step": int(ho.numel() * 8), "steps": e2e_steps, "matches_device_path": e2e_ok,
-               "entry_point": "lgpu_ckks_mulrelin_rescale_batch_host (pinned host buffers, 2-stream chunked pipeline)"}
+               "entry_point": "lgpu_ckks_mulrelin_rescale_batch_host (pinned host buffers, 2-stream chunked pipeline)", "chunk": args.e2e_chunk,
+               "numa": numa, "h2d_GBs": 2 * ha.numel() * 8 * e2e_steps / float(td.item()) / 1e9}
         del ha, hb, ho
     barrier()
 
