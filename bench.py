@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="ciphertext pairs per GPU per step")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="(reference arm) pairs per step; 0 = one per core")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=8, help="ciphertext pairs per pipeline chunk of the host entry point (0 = library default)")
+    ap.add_argument("--e2e-chunk", type=int, default=2, help="ciphertext pairs per pipeline chunk of the host entry point (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="mulrelin", choices=["mulrelin", "bootstrap"],
                     help="bootstrap: BASELINE config 5 -- replay of the op trace of one CKKS bootstrapping (use --preset BOOT_N16QP1767)")
@@ -243,7 +243,7 @@ def gpu_main(args):
     import torch
     import torch.distributed as dist
     import lattigo_b200 as lb
-    from lattigo_b200 import params as presets, _lib
+    from lattigo_b200 import params as presets, _lib, dist as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -271,8 +271,7 @@ def gpu_main(args):
 
     # evaluation key: generated on rank 0, broadcast once over NCCL; never touched again on the hot path
     evk_t = rand_rows(Q + P, (nd, 1, 2)) if rank == 0 else torch.empty((nd, 1, 2, len(Q) + len(P), N), dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(evk_t, src=0)
+    D.broadcast_key(evk_t, src=0)                     # lattigo_b200/dist.py: the plumbing tests/test_multiprocess_cpu.py exercises with gloo
     rlk = lb.GadgetCiphertext(ctx, evk_t, level, levelP)
     ev = lb.CKKSEvaluator(ctx, rlk)
     B = args.batch
@@ -305,11 +304,8 @@ def gpu_main(args):
     launches = _lib.lib().lgpu_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     t_dev = e0.elapsed_time(e1) * 1e-3
-    tt = torch.tensor([t_dev], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_max = float(tt.item())
-    value = B * world * args.steps / t_max
+    t_max = D.max_over_ranks(t_dev, dev)
+    value = D.job_throughput(B * args.steps, t_dev, dev)
 
     # ---- roofline of the dominant kernel class (NTT): same K steps with the event profiler on --------------------
     roof = None
@@ -402,9 +398,7 @@ def gpu_main(args):
             ev.MulRelinRescaleHost(na, nb_, no, chunk=args.e2e_chunk)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        td = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        td = torch.tensor([D.max_over_ranks(dt, dev)], dtype=torch.float64)
         e2e_ok = bool(torch.equal(ho.to(dev), out)) if out is not None else None
         e2e = {"value": B * world * e2e_steps / float(td.item()), "unit": UNIT, "h2d_bytes_per_step": int(2 * ha.numel() * 8),
                "d2h_bytes_per_step": int(ho.numel() * 8), "steps": e2e_steps, "matches_device_path": e2e_ok,
@@ -488,10 +482,8 @@ def bootstrap_main(args):
     barrier()
     launches = _lib.lib().lgpu_launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_max = float(tt.item())
+    from lattigo_b200 import dist as D
+    t_max = D.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
     alg = None
     if rank == 0:
         import ctypes

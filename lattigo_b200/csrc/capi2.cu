@@ -240,7 +240,7 @@ int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64
     if (to_gct(rlk, g)) return -1;
     const Ctx& c = ctx->c;
     REQUIRE(level >= 0 && level < c.nQ && nb_rescales >= 0 && nb_rescales <= level, "level out of range");
-    if (chunk <= 0) chunk = 8;
+    if (chunk <= 0) chunk = 2;   // measured (profiles/r02_e2e_chunks.txt): 547 ct/s at 2, 540 at 4, 515 at 8, 474 at 16 -- short chunks shrink the pipeline's head and tail
     if (chunk > batch) chunk = batch;
     const size_t N = c.N, nq = level + 1, nqo = nq - nb_rescales;
     const size_t in_words = 2 * nq * N, out_words = 2 * nqo * N;
