@@ -174,7 +174,7 @@ enum { PRO_MODUP = 0, PRO_BCAST = 1 };
 #define KS_J 8   // target rows sharing one staged y/v tile
 #endif
 
-template <int RL, int NSMAX, bool FP, int PRO>
+template <int RL, int NSMAX, bool FP, int PRO, bool CORR = true>
 __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStridedParams p) {
     constexpr int R = 1 << RL;
     __shared__ u64 s_c[NSMAX];
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStri
 #pragma unroll
         for (int u = 0; u < RL; u++) {
             const int half = 1 << (RL - 1 - u);
-            const bool corr = (mask >> u) & 1u;
+            const bool corr = CORR && ((mask >> u) & 1u);
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 if (k & half) continue;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256, KS_STRIDED_MINB) ks_strided_kernel(KsStri
 // for J = 4 target rows (thread = (column, target row)): L2 traffic drops 4x, the y reads become conflict-free /
 // broadcast shared-memory loads. Multi-source digits only (the single-limb rule keeps the plain kernel).
 // ------------------------------------------------------------------------------------------------------------
-template <int RL, int NSMAX, bool FP>
+template <int RL, int NSMAX, bool FP, bool CORR = true>
 __global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(KsStridedParams p) {
     constexpr int R = 1 << RL, J = KS_J, LB = 256 / J;
     extern __shared__ u64 dsm[];
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(
 #pragma unroll
         for (int u = 0; u < RL; u++) {
             const int half = 1 << (RL - 1 - u);
-            const bool corr = (mask >> u) & 1u;
+            const bool corr = CORR && ((mask >> u) & 1u);
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 if (k & half) continue;
@@ -744,6 +744,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
 // and the MAC in registers, split mbarrier between digits. The 256 x 16 kernel it replaces (ks_chunk_mac_kernel<false>, kept as
 // LGPU_K3_INT_VARIANT=0) ran 16 warps per SM with CTA-wide barriers and cost 3.3x an FP64 row per row (profiles/r02_configs.json).
 // ------------------------------------------------------------------------------------------------------------
+template <bool CORR>
 __global__ void __launch_bounds__(512, 2) ks_chunk_mac_int8r_kernel(KsChunkParams p) {
     constexpr int CL = 12, T = 512;
     extern __shared__ u64 smem[];
@@ -782,19 +783,19 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_int8r_kernel(KsChunkParam
                 for (int k = 0; k < 8; k++) x[k] = P1row[(size_t)d * p.p1_ds + k * T + tid];
                 if (KS_L2_PREFETCH && dn < p.nd && tid < 256)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(P1row + (size_t)dn * p.p1_ds + tid * 16));
-                int8_bflys<0>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
+                int8_bflys<0, CORR>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
                 if (pending) { mbar_wait(bar, tok); pending = false; }
                 i8s_store_r1(sm, x, tid);
             }
             __syncthreads();
-            i8s_round2(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+            i8s_round2<CORR>(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
             fp8s_pair_sync(tid);
-            i8s_round3(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+            i8s_round3<CORR>(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
             __syncwarp();
             i8s_load_r4(sm, xv, tid);
             tok = mbar_arrive(bar);
             pending = true;
-            int8_bflys<9>(xv, tw, s1, chunk, tid, nq, twoq, kq, mask);     // lazy values below 2 kq: any u64 is a valid MRedLazy operand
+            int8_bflys<9, CORR>(xv, tw, s1, chunk, tid, nq, twoq, kq, mask);     // lazy values below 2 kq: any u64 is a valid MRedLazy operand
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) { const ulonglong2 v = ldg128(xin + 2 * j); xv[2 * j] = v.x; xv[2 * j + 1] = v.y; }
@@ -852,31 +853,32 @@ bool ks_fused_applicable(const Ctx* c, int levelQ, const GadgetCt& evk) {
     return true;
 }
 
-template <int RL, int NSMAX, bool FP>
+template <int RL, int NSMAX, bool FP, bool CORR>
 static int ks_launch_j4(const KsStridedParams& p, dim3 grid, cudaStream_t st) {
     constexpr int R = 1 << RL;
     constexpr int LB = 256 / KS_J;
     const size_t smem = (size_t)NSMAX * R * LB * sizeof(u64) + (size_t)R * LB;
-    LGPU_CUDA_OK(cudaFuncSetAttribute(ks_strided_j4_kernel<RL, NSMAX, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ks_strided_j4_kernel<RL, NSMAX, FP><<<dim3(grid.x * KS_J, (grid.y + KS_J - 1) / KS_J, grid.z), 256, smem, st>>>(p);
+    LGPU_CUDA_OK(cudaFuncSetAttribute(ks_strided_j4_kernel<RL, NSMAX, FP, CORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ks_strided_j4_kernel<RL, NSMAX, FP, CORR><<<dim3(grid.x * KS_J, (grid.y + KS_J - 1) / KS_J, grid.z), 256, smem, st>>>(p);
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <bool FP, int PRO = PRO_MODUP>
+// CORR: the integer rows of the launch need the lazy-correction schedule (some prime above 2^57); ignored for FP64 rows
+template <bool FP, int PRO = PRO_MODUP, bool CORR = true>
 static int ks_launch_strided(int rl, int nsmax, const KsStridedParams& p, dim3 grid, cudaStream_t st) {
     if constexpr (PRO == PRO_MODUP) {
         static const int j4 = [] { const char* e = getenv("LGPU_K2_J4"); return e ? atoi(e) : 1; }();
         bool multi = j4 != 0 && rl <= 4;                       // R = 32 (N = 2^17) would need 2 x 66 KB of shared memory
         for (int d = 0; d < p.nd; d++) multi = multi && (p.dg[d].nS > 1 || !p.single_rule);
         if (multi) {
-#define KS_J4(RLV) case RLV: return nsmax <= 4 ? ks_launch_j4<RLV, 4, FP>(p, grid, st) : ks_launch_j4<RLV, 8, FP>(p, grid, st);
+#define KS_J4(RLV) case RLV: return nsmax <= 4 ? ks_launch_j4<RLV, 4, FP, CORR>(p, grid, st) : ks_launch_j4<RLV, 8, FP, CORR>(p, grid, st);
             switch (rl) { KS_J4(1) KS_J4(2) KS_J4(3) KS_J4(4) default: break; }
 #undef KS_J4
         }
     }
 #define KS_CASE(RLV) \
-    case RLV: if (nsmax <= 4) ks_strided_kernel<RLV, 4, FP, PRO><<<grid, 256, 0, st>>>(p); else ks_strided_kernel<RLV, 8, FP, PRO><<<grid, 256, 0, st>>>(p); break;
+    case RLV: if (nsmax <= 4) ks_strided_kernel<RLV, 4, FP, PRO, CORR><<<grid, 256, 0, st>>>(p); else ks_strided_kernel<RLV, 8, FP, PRO, CORR><<<grid, 256, 0, st>>>(p); break;
     switch (rl) {
         KS_CASE(1) KS_CASE(2) KS_CASE(3) KS_CASE(4) KS_CASE(5)
         default: set_error("unsupported strided radix"); return -1;
@@ -884,6 +886,16 @@ static int ks_launch_strided(int rl, int nsmax, const KsStridedParams& p, dim3 g
 #undef KS_CASE
     LGPU_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// integer rows whose prime needs the lazy-correction schedule (fwd_mask != 0: above 2^57) vs rows that never correct: the second class
+// runs instantiations with the correction compiled out
+static void split_by_corr(const Ctx* c, const RowMap& in, RowMap& corr, RowMap& plain) {
+    corr.nrows = plain.nrows = 0;
+    for (int r = 0; r < in.nrows; r++) {
+        RowMap& d = c->h_limbs[in.limb[r]].fwd_mask != 0 ? corr : plain;
+        d.limb[d.nrows] = in.limb[r]; d.drow[d.nrows] = in.drow[r]; d.nrows++;
+    }
 }
 
 // acc: QP-stacked accumulators (component c, batch b at acc + c*acc_cs + b*acc_bs, rows 0..nq-1 Q then P; canonical).
@@ -966,21 +978,29 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
     const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
     const unsigned chunks = (unsigned)(N >> 12);
     cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
-    if (in.nrows) {
-        sp.rm = in; cp.rm = in;
+    RowMap in_c, in_n;
+    split_by_corr(c, in, in_c, in_n);
+    for (int pass = 0; pass < 2; pass++) {
+        const RowMap& ir = pass ? in_n : in_c;
+        if (!ir.nrows) continue;
+        sp.rm = ir; cp.rm = ir;
         {
-            ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * batch * nd * (double)in.nrows, 1);
-            if (ks_launch_strided<false>(s1, nsmax, sp, dim3(gx, in.nrows, nd * batch), sint)) return -1;
+            ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * batch * nd * (double)ir.nrows, 1);
+            if (pass ? ks_launch_strided<false, PRO_MODUP, false>(s1, nsmax, sp, dim3(gx, ir.nrows, nd * batch), sint)
+                     : ks_launch_strided<false, PRO_MODUP, true>(s1, nsmax, sp, dim3(gx, ir.nrows, nd * batch), sint)) return -1;
         }
-        ProfScope ps(LGPU_KCLASS_MAC, sint, 8.0 * N * in.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
+        ProfScope ps(LGPU_KCLASS_MAC, sint, 8.0 * N * ir.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
         // LGPU_K3_INT_VARIANT=0 selects the 256 x 16 shared-memory-MAC kernel (cross-check of the default 512 x 8 register-MAC one)
         static const int k3i = [] { const char* e = getenv("LGPU_K3_INT_VARIANT"); return e ? atoi(e) : 8; }();
-        if (k3i != 0) {
-            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_int8r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_int8r_kernel<<<dim3(batch, chunks, in.nrows), 512, smem, sint>>>(cp);
+        if (k3i != 0 && pass) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_int8r_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_int8r_kernel<false><<<dim3(batch, chunks, ir.nrows), 512, smem, sint>>>(cp);
+        } else if (k3i != 0) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_int8r_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_int8r_kernel<true><<<dim3(batch, chunks, ir.nrows), 512, smem, sint>>>(cp);
         } else {
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_kernel<false><<<dim3(batch, chunks, in.nrows), 256, smem, sint>>>(cp);
+            ks_chunk_mac_kernel<false><<<dim3(batch, chunks, ir.nrows), 256, smem, sint>>>(cp);
         }
         LGPU_CUDA_OK(cudaGetLastError());
     }
@@ -1164,6 +1184,7 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
 }
 
 // integer-row variant of fz_chunk_epi_fp8_kernel (512 threads x 8 elements, last round and epilogue in registers)
+template <bool CORR>
 __global__ void __launch_bounds__(512, 2) fz_chunk_epi_int8_kernel(FzChunkParams p) {
     constexpr int CL = 12, T = 512;
     extern __shared__ u64 smem[];
@@ -1188,13 +1209,13 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_int8_kernel(FzChunkParams
         u64 x[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) x[k] = src[k * T + tid];
-        int8_bflys<0>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
+        int8_bflys<0, CORR>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
         i8s_store_r1(sm, x, tid);
     }
     __syncthreads();
-    i8s_round2(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+    i8s_round2<CORR>(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
     fp8s_pair_sync(tid);
-    i8s_round3(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+    i8s_round3<CORR>(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
     ulonglong2 a[4], d[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -1204,7 +1225,7 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_int8_kernel(FzChunkParams
     __syncwarp();
     u64 x[8];
     i8s_load_r4(sm, x, tid);
-    int8_bflys<9>(x, tw, s1, chunk, tid, nq, twoq, kq, mask);
+    int8_bflys<9, CORR>(x, tw, s1, chunk, tid, nq, twoq, kq, mask);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         // lazy transform output below 2 kq (up to ~2^64 for 60 / 61-bit primes): one correction keeps x + 2q - a inside 64 bits
@@ -1218,7 +1239,7 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_int8_kernel(FzChunkParams
     }
 }
 
-template <bool FP>
+template <bool FP, bool CORR = true>
 static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
     const size_t smem = (size_t)(4096 + 256 + 8) * sizeof(u64);
     static const int v8 = [] { const char* e = getenv("LGPU_FZ_VARIANT"); return e ? atoi(e) : 8; }();
@@ -1230,7 +1251,7 @@ static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
         return 0;
     }
     if (!FP && v8 == 8 && vec_ok) {
-        fz_chunk_epi_int8_kernel<<<grid, 512, smem, st>>>(p);
+        fz_chunk_epi_int8_kernel<CORR><<<grid, 512, smem, st>>>(p);
         LGPU_CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -1317,11 +1338,18 @@ int moddown_ntt_fused(const Ctx* c, int levelQ, int levelP, const u64* acc, size
     const unsigned chunks = (unsigned)(N >> 12);
     auto scal = [&](const RowMap& rm) { for (int r = 0; r < rm.nrows; r++) { const int i = rm.drow[r]; cp.s[r] = c->Q[i] - c->mdc_PtoQ[(size_t)levelP * c->nQ + i]; } };
     cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
-    if (in.nrows) {
-        { ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows, 1);
-          sp.rm = in; if (ks_launch_strided<false>(s1, np, sp, dim3(gx, in.nrows, Z), sint)) return -1; }
-        ProfScope ps(LGPU_KCLASS_EPILOGUE, sint, 8.0 * N * Z * in.nrows * ((D ? 5.0 : 4.0) - 1.0), 1);
-        cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), sint)) return -1;
+    RowMap in_c, in_n;
+    split_by_corr(c, in, in_c, in_n);
+    for (int pass = 0; pass < 2; pass++) {
+        const RowMap& ir = pass ? in_n : in_c;
+        if (!ir.nrows) continue;
+        { ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * ir.nrows, 1);
+          sp.rm = ir;
+          if (pass ? ks_launch_strided<false, PRO_MODUP, false>(s1, np, sp, dim3(gx, ir.nrows, Z), sint)
+                   : ks_launch_strided<false, PRO_MODUP, true>(s1, np, sp, dim3(gx, ir.nrows, Z), sint)) return -1; }
+        ProfScope ps(LGPU_KCLASS_EPILOGUE, sint, 8.0 * N * Z * ir.nrows * ((D ? 5.0 : 4.0) - 1.0), 1);
+        cp.rm = ir; scal(ir);
+        if (pass ? fz_launch_chunk<false, false>(cp, dim3(chunks, ir.nrows, Z), sint) : fz_launch_chunk<false, true>(cp, dim3(chunks, ir.nrows, Z), sint)) return -1;
     }
     if (fp.nrows) {
         { ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows, 1);
@@ -1370,11 +1398,18 @@ int div_round_last_ntt_fused(const Ctx* c, int level, const u64* X, size_t x_cs,
     auto s0 = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) { const u64 qi = c->Q[rm.drow[k]]; sp.s0[k] = qi - (pHalf % qi); } };
     auto scal = [&](const RowMap& rm) { for (int k = 0; k < rm.nrows; k++) cp.s[k] = c->rescaleQ[(size_t)(level - 1) * c->nQ + rm.drow[k]]; };
     cudaStream_t sint = fork_side(c, st, fp.nrows > 0 && in.nrows > 0);
-    if (in.nrows) {
-        { ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * in.nrows, 1);
-          sp.rm = in; s0(in); if (ks_launch_strided<false, PRO_BCAST>(s1, 1, sp, dim3(gx, in.nrows, Z), sint)) return -1; }
-        ProfScope ps(LGPU_KCLASS_EPILOGUE, sint, 8.0 * N * Z * in.nrows * (4.0 - 1.0), 1);
-        cp.rm = in; scal(in); if (fz_launch_chunk<false>(cp, dim3(chunks, in.nrows, Z), sint)) return -1;
+    RowMap in_c, in_n;
+    split_by_corr(c, in, in_c, in_n);
+    for (int pass = 0; pass < 2; pass++) {
+        const RowMap& ir = pass ? in_n : in_c;
+        if (!ir.nrows) continue;
+        { ProfScope ps(LGPU_KCLASS_FUSED, sint, 8.0 * N * Z * ir.nrows, 1);
+          sp.rm = ir; s0(ir);
+          if (pass ? ks_launch_strided<false, PRO_BCAST, false>(s1, 1, sp, dim3(gx, ir.nrows, Z), sint)
+                   : ks_launch_strided<false, PRO_BCAST, true>(s1, 1, sp, dim3(gx, ir.nrows, Z), sint)) return -1; }
+        ProfScope ps(LGPU_KCLASS_EPILOGUE, sint, 8.0 * N * Z * ir.nrows * (4.0 - 1.0), 1);
+        cp.rm = ir; scal(ir);
+        if (pass ? fz_launch_chunk<false, false>(cp, dim3(chunks, ir.nrows, Z), sint) : fz_launch_chunk<false, true>(cp, dim3(chunks, ir.nrows, Z), sint)) return -1;
     }
     if (fp.nrows) {
         { ProfScope ps(LGPU_KCLASS_FUSED, st, 8.0 * N * Z * fp.nrows, 1);

@@ -505,13 +505,14 @@ __device__ __forceinline__ void fp8s_load_r4(const double* fsm, double (&x)[8], 
 // ---- the same four radix-8 rounds for the integer (Shoup) butterflies: 512 threads x 8 elements on the XOR-swizzled u64 tile. Twiddle pairs are
 // read where they are used (16 bytes each, L1-resident; rounds 1-2 are warp-uniform) instead of being held in 28 registers. `mask` is the
 // prime's lazy-correction schedule (LimbConst.fwd_mask: 0 below 2^57, every other stage for 60-bit primes, every stage for 61-bit ones).
-template <int A>
+// CORR = false compiles the correction out (launches whose primes all have an empty schedule: q0 and the 55-bit special primes of the CKKS sets).
+template <int A, bool CORR = true>
 __device__ __forceinline__ void int8_bflys(u64 (&x)[8], const ulonglong2* tw, int s1, int chunk, int hi, u64 nq, u64 twoq, u64 kq, unsigned mask) {
 #pragma unroll
     for (int u = 0; u < 3; u++) {
         const int half = 4 >> u;
         const int twbase = (1 << (s1 + A + u)) + (chunk << (A + u)) + (hi << u);
-        const bool corr = (mask >> (s1 + A + u)) & 1u;
+        const bool corr = CORR && ((mask >> (s1 + A + u)) & 1u);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (k & half) continue;
@@ -524,6 +525,7 @@ __device__ __forceinline__ void i8s_store_r1(u64* sm, const u64 (&x)[8], int tid
 #pragma unroll
     for (int k = 0; k < 8; k++) a[512 * k] = x[k];
 }
+template <bool CORR = true>
 __device__ __forceinline__ void i8s_round2(u64* sm, const ulonglong2* tw, int s1, int chunk, int tid, u64 nq, u64 twoq, u64 kq, unsigned mask) {
     const int tb = swz(((tid >> 6) << 9) + (tid & 63));
     u64* a0 = sm + tb;
@@ -531,10 +533,11 @@ __device__ __forceinline__ void i8s_round2(u64* sm, const ulonglong2* tw, int s1
     u64 x[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) x[k] = ((k & 1) ? a1 : a0)[64 * k];
-    int8_bflys<3>(x, tw, s1, chunk, tid >> 6, nq, twoq, kq, mask);
+    int8_bflys<3, CORR>(x, tw, s1, chunk, tid >> 6, nq, twoq, kq, mask);
 #pragma unroll
     for (int k = 0; k < 8; k++) ((k & 1) ? a1 : a0)[64 * k] = x[k];
 }
+template <bool CORR = true>
 __device__ __forceinline__ void i8s_round3(u64* sm, const ulonglong2* tw, int s1, int chunk, int tid, u64 nq, u64 twoq, u64 kq, unsigned mask) {
     const int tb = swz(((tid >> 3) << 6) + (tid & 7));
     u64* a[8];
@@ -543,7 +546,7 @@ __device__ __forceinline__ void i8s_round3(u64* sm, const ulonglong2* tw, int s1
     u64 x[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) x[k] = *a[k];
-    int8_bflys<6>(x, tw, s1, chunk, tid >> 3, nq, twoq, kq, mask);
+    int8_bflys<6, CORR>(x, tw, s1, chunk, tid >> 3, nq, twoq, kq, mask);
 #pragma unroll
     for (int k = 0; k < 8; k++) *a[k] = x[k];
 }

@@ -470,7 +470,7 @@ struct IntFwdOps {
 // one CTA barrier, pair / warp exchanges, coalesced copy-out of canonical residues). The 256 x 16 IntFwdOps ran 16 warps per SM at 128
 // registers; this one runs 32 at 64. The per-prime correction schedule is evaluated at run time (all-zero below 2^57).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int RL>
+template <int RL, bool CORR>
 struct IntFwdOps2 {
     static constexpr int T = 512, MINB = 2;
     static constexpr bool kInverse = false;
@@ -493,7 +493,7 @@ struct IntFwdOps2 {
 #pragma unroll
         for (int u = 0; u < RL; u++) {
             const int half = 1 << (RL - 1 - u);
-            const bool corr = (mask >> u) & 1u;
+            const bool corr = CORR && ((mask >> u) & 1u);
 #pragma unroll
             for (int k = 0; k < R; k++) {
                 if (k & half) continue;
@@ -517,20 +517,20 @@ struct IntFwdOps2 {
             u64 x[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = __ldcg(io + k * T + tid);
-            int8_bflys<0>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
+            int8_bflys<0, CORR>(x, tw, s1, chunk, 0, nq, twoq, kq, mask);
             i8s_store_r1(sm, x, tid);
         }
         __syncthreads();
-        i8s_round2(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+        i8s_round2<CORR>(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
         fp8s_pair_sync(tid);
-        i8s_round3(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
+        i8s_round3<CORR>(sm, tw, s1, chunk, tid, nq, twoq, kq, mask);
         __syncwarp();
         {
             const int tb = swz(tid << 3);
             u64 x[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = sm[tb ^ k];
-            int8_bflys<9>(x, tw, s1, chunk, tid, nq, twoq, kq, mask);
+            int8_bflys<9, CORR>(x, tw, s1, chunk, tid, nq, twoq, kq, mask);
 #pragma unroll
             for (int k = 0; k < 8; k++) sm[tb ^ k] = bred_add(x[k], q, bhi);            // reducevec, ring/ntt.go:176
         }
@@ -922,7 +922,8 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
             if (pv == 2) return persist_launch<FpFwdOps<RLV, 0>, true>(c, rm, in, out, batch, st, mul);                      \
             return persist_launch<FpFwdOps<RLV, 0>>(c, rm, in, out, batch, st, mul);                                         \
         }                                                                                                               \
-        if (!inverse && piv >= 3) return persist_launch<IntFwdOps2<RLV>, true>(c, rm, in, out, batch, st, mul);              \
+        if (!inverse && piv >= 3) return kind == 1 ? persist_launch<IntFwdOps2<RLV, true>, true>(c, rm, in, out, batch, st, mul)  \
+                                                   : persist_launch<IntFwdOps2<RLV, false>, true>(c, rm, in, out, batch, st, mul); \
         if (pv >= 2) {                                                                                                  \
             if (kind == 1) return inverse ? persist_launch<IntInvOps<RLV, 1>, true>(c, rm, in, out, batch, st, mul)          \
                                           : persist_launch<IntFwdOps<RLV, 1>, true>(c, rm, in, out, batch, st, mul);         \
