@@ -1,5 +1,6 @@
 // capi3.cu -- extern "C" entry points of the rows that sit right above the key-switch path: hoisted linear
 // transformations (lintrans.cu).
+#include <map>
 #include <vector>
 #include "capi_common.h"
 #include "composite.h"
@@ -69,6 +70,84 @@ int lgpu_rgsw_external_product(lgpu_ctx* ctx, const uint64_t* ct_in, int level_i
     u64* out = (u64*)ct_out;
     return rgsw_external_product(&ctx->c, g0, g1, CSpan{in, N, 2 * ci}, CSpan{in + ci, N, 2 * ci}, Span{out, N, 2 * co}, Span{out + co, N, 2 * co}, batch,
                                  S(stream));
+}
+
+// blindrot.Evaluator.BlindRotateCore (core/rgsw/blindrot/evaluator.go:144-203) + evaluateFromDiscreteLogSets (:206-229) +
+// getGaloisElementInverseMap / getDiscreteLogSets (:232-283): Algorithm 3 of eprint 2022/198 on one accumulator. The control flow is driven by the
+// LWE mask `a` (HOST, values modulo 2N, odd or zero); every step is an evaluator call that is already on the device (Evaluator.Automorphism with the
+// window keys, rgsw ExternalProduct with RGSW(X^{s_j})), in place on `acc`.
+int lgpu_blind_rotate_core(lgpu_ctx* ctx, const uint64_t* a_host, int n_lwe, uint64_t* acc, int level, const lgpu_gadget_ct* brk0, const lgpu_gadget_ct* brk1,
+                           const lgpu_galois_keys* gks, int window_size, void* stream) {
+    REQUIRE_DEVICE(ctx);
+    REQUIRE(a_host && acc && brk0 && brk1 && gks && n_lwe >= 1, "null argument");
+    REQUIRE_ALIGNED(AL(acc));
+    REQUIRE(window_size >= 1, "window size must be positive");
+    const Ctx& c = ctx->c;
+    REQUIRE(c.ring_type == 0, "blind rotation is defined on the standard ring");
+    REQUIRE(level >= 0 && level < c.nQ, "level out of range");
+    const long long N = c.N, twoN = 2 * N, Nhalf = N >> 1;
+    // map[(+/-) g^k mod 2N] = +/- k   (:232-258)
+    std::vector<long long> dlog((size_t)twoN, 0);
+    std::vector<char> has((size_t)twoN, 0);
+    {
+        unsigned long long pw = 1;
+        for (long long i = 0; i < Nhalf; i++) {
+            dlog[pw] = i; has[pw] = 1;
+            dlog[(size_t)(twoN - (long long)pw)] = -i; has[(size_t)(twoN - (long long)pw)] = 1;
+            pw = pw * 5 & (unsigned long long)(twoN - 1);
+        }
+    }
+    // discrete-log sets of a (:261-283); Go's map lookup of a[i] = 0 yields the zero value 0
+    std::map<long long, std::vector<int>> sets;
+    for (int i = 0; i < n_lwe; i++) {
+        const unsigned long long ai = a_host[i];
+        REQUIRE(ai < (unsigned long long)twoN, "blind rotation: a[i] is not reduced modulo 2N");
+        REQUIRE((ai & 1) == 1 || ai == 0, "getDiscreteLogSets: a[i] is not odd and thus not an element of Z_{2N}^{*} -> a[i] = (+/- 1) * g^{k} does not exist.");
+        sets[has[ai] ? dlog[ai] : 0].push_back(i);
+    }
+    GaloisKeySet ks;
+    ks.n = gks->n_keys; ks.gal_els = (const u64*)gks->gal_els;
+    ks.keys.resize(ks.n);
+    for (int i = 0; i < ks.n; i++) if (to_gct3(&gks->keys[i], ks.keys[i])) return -1;
+    const size_t nq = level + 1, cs = nq * (size_t)N;
+    u64* A = (u64*)acc;
+    cudaStream_t st = S(stream);
+    auto automorph = [&](long long k) -> int {     // eval.Automorphism(acc, GaloisElement(k), acc)
+        const u64 g = galois_element(&c, k);
+        const GadgetCt* gk = ks.find(g);
+        if (!gk) return -1;
+        return evaluator_automorphism(&c, level, CSpan{A, (size_t)N, 2 * cs}, CSpan{A + cs, (size_t)N, 2 * cs}, g, *gk, Span{A, (size_t)N, 2 * cs},
+                                      Span{A + cs, (size_t)N, 2 * cs}, nullptr, 1, st);
+    };
+    auto from_sets = [&](long long k, int v, int& vout) -> int {
+        auto it = sets.find(k);
+        if (it != sets.end()) {
+            if (v != 0) { if (automorph(v)) return -1; v = 0; }
+            for (int j : it->second) {
+                GadgetCt g0, g1;
+                if (to_gct3(&brk0[j], g0) || to_gct3(&brk1[j], g1)) return -1;
+                if (rgsw_external_product(&c, g0, g1, CSpan{A, (size_t)N, 2 * cs}, CSpan{A + cs, (size_t)N, 2 * cs}, Span{A, (size_t)N, 2 * cs},
+                                          Span{A + cs, (size_t)N, 2 * cs}, 1, st)) return -1;
+            }
+        }
+        v++;
+        if (v == window_size || k == 1) { if (automorph(v)) return -1; v = 0; }
+        vout = v;
+        return 0;
+    };
+    int v = 0, dummy = 0;
+    for (long long i = Nhalf - 1; i > 0; i--) if (from_sets(-i, v, v)) return -1;          // lines 3-9
+    if (from_sets(twoN, 0, dummy)) return -1;                                              // line 10 (never in the sets: 2N is not a residue)
+    {                                                                                      // line 12: acc = acc(X^{-g})
+        const u64 g = c.nthroot - 5;
+        const GadgetCt* gk = ks.find(g);
+        if (!gk) return -1;
+        if (evaluator_automorphism(&c, level, CSpan{A, (size_t)N, 2 * cs}, CSpan{A + cs, (size_t)N, 2 * cs}, g, *gk, Span{A, (size_t)N, 2 * cs},
+                                   Span{A + cs, (size_t)N, 2 * cs}, nullptr, 1, st)) return -1;
+    }
+    for (long long i = Nhalf - 1; i > 0; i--) if (from_sets(i, v, v)) return -1;           // lines 13-19
+    if (from_sets(0, 0, dummy)) return -1;                                                 // lines 20-21
+    return 0;
 }
 
 int lgpu_evaluator_automorphism_hoisted_lazy(lgpu_ctx* ctx, int level_q, const uint64_t* ct0, const uint64_t* decomp, int decomp_level_q,

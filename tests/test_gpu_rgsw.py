@@ -65,3 +65,39 @@ def test_external_product_without_p_and_32_bit_path():
 def test_external_product_fused_sizes():
     q, p = O.gen_moduli(14, [56, 45, 45, 45, 45, 45], [55, 55])
     _case(13, q, p, 0, 10)
+
+
+@pytest.mark.parametrize("lp,pw2", [([50], 0), ([50, 50], 0), ([], 10)])
+def test_blind_rotate_core_matches_the_oracle(lp, pw2):
+    """lgpu_blind_rotate_core == oracle/blindrot.py (core/rgsw/blindrot/evaluator.go:144-283) bit for bit: uniform accumulator and keys, masks with
+    repeated discrete logs, a zero entry, and window boundaries; the three ExternalProduct paths underneath."""
+    import torch
+    import lattigo_b200 as lb
+    from oracle import blindrot as BR
+    logN, n_lwe, window = 8, 24, 4
+    q, p = O.gen_moduli(logN + 1, [50, 45], lp)
+    params = O.Parameters(logN, q, p)
+    N = params.N()
+    rng = np.random.default_rng(len(lp) * 7 + pw2)
+    levelQ, levelP = len(q) - 1, len(p) - 1
+    brk_o = [[H.random_gadget_ciphertext(params, levelQ, levelP, rng, pw2=pw2) for _ in range(2)] for _ in range(n_lwe)]
+    gals = [params.GaloisElement(k) for k in range(1, window + 1)] + [2 * N - 5]
+    gks_o = {g: H.random_gadget_ciphertext(params, levelQ, levelP, rng, pw2=pw2) for g in gals}
+    a = rng.integers(0, N, n_lwe, dtype=np.uint64) * 2 + 1
+    a[3] = 0; a[5] = a[7]; a[9] = 1; a[11] = 2 * N - 1
+    acc = np.stack([H.rand_poly(q, N, rng), H.rand_poly(q, N, rng)])
+    want = [acc[0].copy(), acc[1].copy()]
+    BR.Evaluator(params, window).BlindRotateCore(a, want, brk_o, gks_o)
+    ctx = lb.Context(logN, q, p)
+    try:
+        mk = lambda g: lb.GadgetCiphertext(ctx, g.data, levelQ, levelP, pw2, g.pw2_sizes)
+        ev = lb.rgsw.BlindRotationEvaluator(ctx, [lb.rgsw.Ciphertext(mk(b[0]), mk(b[1])) for b in brk_o], {g: mk(k) for g, k in gks_o.items()}, window)
+        d = ctx.to_device(acc)
+        ev.BlindRotateCore(a, d)
+        got = ctx.to_host(d)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        ev2 = lb.rgsw.BlindRotationEvaluator(ctx, ev.brk, {g: k for g, k in ev.keys.items() if g != gals[1]}, window)
+        with pytest.raises(lb.LgpuError, match="GaloisKey"):
+            ev2.BlindRotateCore(a, ctx.to_device(acc))
+    finally:
+        ctx.close()
