@@ -345,6 +345,12 @@ int lgpu_gen_evaluation_key(lgpu_ctx* ctx, const uint64_t* sk_in, const uint64_t
  * (GaloisElement(1..window_size) and NthRoot - GaloisGen; a missing one is an error). window_size = 10 in the reference (keys.go:14). */
 int lgpu_blind_rotate_core(lgpu_ctx* ctx, const uint64_t* a_host, int n_lwe, uint64_t* acc, int level, const lgpu_gadget_ct* brk0,
                            const lgpu_gadget_ct* brk1, const lgpu_galois_keys* gks, int window_size, void* stream);
+/* ckks.SpecialFFTDouble / SpecialIFFTDouble (schemes/ckks/ckks_vector_ops.go:18-77; Encoder.FFT / IFFT, schemes/ckks/encoder.go:764-816), in
+ * place on `batch` vectors of n complex128 values (device, interleaved re / im, batch_stride in complex values). rot_group (n int64 values)
+ * and roots (m + 1 complex128 values) are the encoder's own tables (encoder.go:83-112), device resident. Same operations in the same order
+ * as the Go code and no fused multiply-add: results are bit-identical on identical tables. */
+int lgpu_ckks_special_fft(lgpu_ctx* ctx, double* values, int n, int m, const int64_t* rot_group, const double* roots, int inverse,
+                          int batch, size_t batch_stride, void* stream);
 
 /* ---- wire format -> device (the reference's WriteTo / ReadFrom byte streams, little-endian uint64 words) ------------------
  * ring.Poly (ring/poly.go:132-179): rows, then per row {len, len words}. */

@@ -11,3 +11,4 @@ from . import lintrans  # noqa: F401,E402
 from . import wire  # noqa: F401,E402
 from . import rgsw  # noqa: F401,E402
 from . import encryptor  # noqa: F401,E402
+from . import ckks_fft  # noqa: F401,E402
