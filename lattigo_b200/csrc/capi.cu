@@ -35,7 +35,7 @@ int make_rowmap_single(const Ctx& c, int ring, int limb, RowMap& rm) {
 
 extern "C" {
 
-const char* lgpu_version(void) { return "lattigo_b200 0.1 (sm_100a)"; }
+const char* lgpu_version(void) { return "lattigo_b200 0.2 (sm_100a)"; }
 const char* lgpu_last_error(void) { return lgpu::last_error(); }
 
 int lgpu_create(lgpu_ctx** out, int device, int logN, int ring_type, const uint64_t* q, int nq, const uint64_t* p, int np) {
