@@ -712,14 +712,14 @@ __global__ void __launch_bounds__(256) ckks_tensor_kernel(TensorParams p) {
 static int ckks_mulrelin_rescale_chunk(const Ctx* c, int level, const u64* ctA, const u64* ctB, const GadgetCt& rlk, int nb_rescales,
                                        u64* out, int batch, cudaStream_t st);
 
-// Sub-batches keep the per-ciphertext intermediates (a few hundred MB per ciphertext at N = 2^16) flowing through
-// the 126 MB L2 instead of HBM between the passes of one transform; the evaluation key is re-streamed once per
-// sub-batch. LGPU_BATCH_CHUNK overrides the default.
+// Sub-batches bound the key-switch scratch (P1 is 270 MB per ciphertext at L = 44: 17 GB for 64) while the evaluation key is streamed
+// once per sub-batch. Measured at L = 44, batch 64 (profiles/README.md): 1 542 ct/s with sub-batches of 16, 1 573 with 32, 1 584 with 64.
+// LGPU_BATCH_CHUNK overrides the default.
 static int batch_chunk() {
     static int v = [] {
         const char* e = getenv("LGPU_BATCH_CHUNK");
-        int x = e ? atoi(e) : 32;
-        return x > 0 ? x : 32;
+        int x = e ? atoi(e) : 64;
+        return x > 0 ? x : 64;
     }();
     return v;
 }
