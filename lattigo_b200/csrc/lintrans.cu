@@ -335,8 +335,8 @@ static int multiply_naive(const LtState& s, const LinTransView& m, int levelQ, u
     if (!keys.empty() && keys[0] == 0) { state = true; keys.erase(keys.begin()); }
     const size_t per = (size_t)2 * s.batch * (nq + np) * N;
     Scratch buf;
-    if (buf.alloc(2 * per + N, s.st)) return -1;
-    u64* cb = buf.p; u64* ab = buf.p + per; u64* index = buf.p + 2 * per;
+    if (buf.alloc(2 * per, s.st)) return -1;
+    u64* cb = buf.p; u64* ab = buf.p + per;
     AccSpans acc = stacked_acc(ab, nq, np, N, s.batch);
     const size_t cs = (size_t)(out_level + 1) * N;
     for (size_t i = 0; i < keys.size(); i++) {
@@ -470,7 +470,6 @@ static int multiply_bsgs(const LtState& s, const LinTransView& m, const PreRot& 
 int lintrans_evaluate_many(const Ctx* c, int level_in, const u64* ct_in, const LinTransView* mats, int n_mats, const GaloisKeySet& gks,
                            u64* const* outs, int* out_levels, int batch, cudaStream_t st) {
     if (n_mats < 1) { set_error("no linear transformation"); return -1; }
-    if (c->ring_type != 0 && false) return -1;
     if (level_in < 0 || level_in >= c->nQ) { set_error("ciphertext level out of range"); return -1; }
     int levelQd = 0;
     const int levelP = mats[0].level_p;
