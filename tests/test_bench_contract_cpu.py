@@ -34,3 +34,13 @@ def test_product_arm_needs_cuda():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0                      # loud failure, never a silent CPU path
     assert not any(l.startswith("{") for l in r.stdout.splitlines())
+
+
+def test_bootstrap_workload_reference_arm_is_declared_unavailable():
+    """BASELINE config 5 is an op-trace replay of the device path; there is no CPU restatement of circuits/ckks/bootstrapping, and the
+    reference arm says so in the contract's `unavailable` form instead of timing something else."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "bootstrap", "--preset", "BOOT_N16QP1767"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and "unavailable" in line
