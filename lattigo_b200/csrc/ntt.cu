@@ -288,6 +288,11 @@ static int fast_variant(const Ctx* c, const RowMap& rm, bool inverse) {
     return 2;
 }
 
+static bool persist_worthwhile(int limb_transforms) {
+    static const int forced = [] { const char* e = getenv("LGPU_NTT_PERSIST"); return e ? atoi(e) : -1; }();
+    return forced == 1 || limb_transforms >= 64;
+}
+
 static int check_common(const Ctx* c, const RowMap& rm, int batch) {
     if (c->logN < 4 || c->logN > 17) { set_error("NTT requires 16 <= N <= 2^17"); return -1; }
     if (rm.nrows <= 0 || rm.nrows > kMaxRows || batch <= 0 || batch > 65535) { set_error("bad rows/batch"); return -1; }
@@ -312,7 +317,9 @@ int launch_ntt(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, in
     if (check_common(c, rm, batch)) return -1;
     if (c->ring_type != 0) return launch_ntt_ci(c, rm, false, in, out, batch, mode == NTT_EXACT_LAZY, st);
     RowMap fp, rest;
-    const bool persist = mode == NTT_CANONICAL && ntt_persist_supported(c, false);
+    // the tile queue pays a fill / drain of ~D limb-transforms: below ~2 waves of work the two-pass kernels are faster (one polynomial of 44 limbs:
+    // 12.4 % vs 10.6 % of the HBM roofline, profiles/r02_ntt_ab.json)
+    const bool persist = mode == NTT_CANONICAL && ntt_persist_supported(c, false) && persist_worthwhile(rm.nrows * batch);
     // the two-pass FP64 forward chunk pass stores 128 bits at a time; the persistent kernels use 64-bit accesses only
     const bool vec_ok = persist || (aligned16(out.p) && even_words(out.row_stride, out.batch_stride));
     if (mode == NTT_CANONICAL && vec_ok && split_rows_fp64(c, rm, fp, rest)) {
@@ -377,7 +384,7 @@ static int launch_ntt_int(const Ctx* c, const RowMap& rm, CSpan in, Span out, in
     const int cl = c->logN > 12 ? 12 : c->logN;
     const int s1 = c->logN - cl;
     const int fast = (mode == NTT_CANONICAL) ? fast_variant(c, rm, false) : 0;
-    const bool persist = fast != 0 && ntt_persist_supported(c, false);
+    const bool persist = fast != 0 && ntt_persist_supported(c, false) && persist_worthwhile(rm.nrows * batch);
     ProfScope ps(LGPU_KCLASS_NTT_FWD, st, 16.0 * c->N * rm.nrows * batch, (s1 > 0 && !persist) ? 2 : 1);
     if (persist) return launch_ntt_persist(c, rm, false, fast, in, out, batch, st);
     if (s1 > 0) {

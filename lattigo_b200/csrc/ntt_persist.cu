@@ -316,8 +316,17 @@ struct FpFwdOps2 : FpFwdOps<RL, 0> {
 #pragma unroll
             for (int k = 0; k < 8; k++) x[k] = *a[k];
             fp8_bflys(x, tt, fq, fqinv);
+#ifdef NTT_CANON_INT
+            // A/B (tools/build_variant.sh canon_int ntt_persist.cu -DNTT_CANON_INT): canonicalise on the integer pipes (one biased conversion + one
+            // Barrett step) instead of 5 FP64 operations per coefficient
+            const double off52 = __dmul_rn((double)(10 + p.logN), fq) + 4503599627370496.0;
+            const u64 qi = L.q, bhi = L.bred_hi;
+#pragma unroll
+            for (int k = 0; k < 8; k++) *reinterpret_cast<u64*>(a[k]) = bred_add(fp_biased_u64(x[k], off52), qi, bhi);
+#else
 #pragma unroll
             for (int k = 0; k < 8; k++) *reinterpret_cast<u64*>(a[k]) = fp_canon(x[k], fq, fqinv);
+#endif
         }
         __syncwarp();
         {   // this warp's 256 consecutive coefficients, 256 B per store instruction; swzc(32 m) = 32 m ^ ((m & 1) << 2) ^ (((m >> 1) & 1) * 9)

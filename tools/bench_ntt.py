@@ -84,7 +84,7 @@ def main():
     for spec in filter(None, args.extra.split(";")):
         name, kv = spec.split(":")
         variants[name] = dict(x.split("=") for x in kv.split(","))
-    names = args.variants.split(",") if args.variants else list(variants)
+    names = (args.variants.split(",") if args.variants else list(VARIANTS)) + [n for n in variants if n not in VARIANTS]
     out = {}
     for v in names:
         env = dict(os.environ, **variants[v])
