@@ -278,6 +278,11 @@ static int launch_strided(int rl, const NttParams& p, int rows, int batch, cudaS
     return 0;
 }
 
+static bool persist_worthwhile(int limb_transforms) {
+    static const int forced = [] { const char* e = getenv("LGPU_NTT_PERSIST"); return e ? atoi(e) : -1; }();
+    return forced == 1 || limb_transforms >= 64;
+}
+
 // 2 = every limb of the launch needs no lazy correction at all (forward: fwd_mask == 0; inverse: inv_lazy), so the
 // correction code is compiled out; 1 = per-limb schedules evaluated at run time.
 static int fast_variant(const Ctx* c, const RowMap& rm, bool inverse) {
@@ -286,11 +291,6 @@ static int fast_variant(const Ctx* c, const RowMap& rm, bool inverse) {
         if (inverse ? (L.inv_lazy == 0) : (L.fwd_mask != 0)) return 1;
     }
     return 2;
-}
-
-static bool persist_worthwhile(int limb_transforms) {
-    static const int forced = [] { const char* e = getenv("LGPU_NTT_PERSIST"); return e ? atoi(e) : -1; }();
-    return forced == 1 || limb_transforms >= 64;
 }
 
 static int check_common(const Ctx* c, const RowMap& rm, int batch) {
@@ -339,7 +339,7 @@ int launch_ntt_mul_montgomery(const Ctx* c, const RowMap& rm, CSpan in, CSpan ot
     if (check_common(c, rm, batch)) return -1;
     if (!other.p) { set_error("null operand"); return -1; }
     if (other.p == out.p) { set_error("NTT+MulCoeffsMontgomery: the multiplicand cannot be the output"); return -1; }
-    if (c->ring_type == 0 && ntt_persist_supported(c, false)) {
+    if (c->ring_type == 0 && ntt_persist_supported(c, false) && persist_worthwhile(rm.nrows * batch)) {
         RowMap fp, rest;
         if (!split_rows_fp64(c, rm, fp, rest)) { rest = rm; fp.nrows = 0; }
         if (fp.nrows > 0) {

@@ -226,7 +226,7 @@ def test_ntt_then_mul_coeffs_montgomery_fused(logN, family):
     ctx = lb.Context(logN, Q)
     rq = ctx.ringQ
     rng = np.random.default_rng(logN)
-    batch = 3
+    batch = 13                                                 # rows x batch >= 64: the persistent (fused-epilogue) kernels; fewer take two launches
     a = np.stack([H.rand_poly(Q, N, rng) for _ in range(batch)])
     for i, q in enumerate(Q):
         if q < (1 << 58):
@@ -241,6 +241,9 @@ def test_ntt_then_mul_coeffs_montgomery_fused(logN, family):
     ring = O.Ring(N, Q)
     want = np.empty_like(a[1]); ring.NTT(a[1], want); ring.MulCoeffsMontgomery(want, b[1], want)
     assert np.array_equal(ctx.to_host(fused)[1], want)
+    small = rq.NewPoly(2)                                       # below the persistent kernels' threshold: transform + coefficient-wise kernel
+    rq.NTTThenMulCoeffsMontgomery(da[:2].contiguous(), db[:2].contiguous(), small)
+    assert np.array_equal(ctx.to_host(small), ctx.to_host(ref)[:2])
     # in place (in == out) and the aliasing error
     inpl = da.clone()
     rq.NTTThenMulCoeffsMontgomery(inpl, db, inpl)
