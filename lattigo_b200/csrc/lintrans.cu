@@ -117,7 +117,7 @@ struct HoistParams {
     int nq, np, nQfull, nd, n, batch;
 };
 constexpr int kHoistB = 4;   // batch elements per thread: the key words are loaded once for all of them
-__global__ void __launch_bounds__(256, 4) lt_hoisted_auto_kernel(HoistParams p) {
+__global__ void __launch_bounds__(256) lt_hoisted_auto_kernel(HoistParams p) {
     const int r = blockIdx.y;
     const bool isP = r >= p.nq;
     const int jr = isP ? r - p.nq : r;
@@ -132,9 +132,8 @@ __global__ void __launch_bounds__(256, 4) lt_hoisted_auto_kernel(HoistParams p) 
         u64 a0[kHoistB], a1[kHoistB];
 #pragma unroll
         for (int t = 0; t < kHoistB; t++) { a0[t] = 0; a1[t] = 0; }
-        // ncu (profiles/r02_ncu_lintrans_summary.csv): DRAM traffic = decomposition once + key once per group + outputs (the gather costs no
-        // extra sectors), 38 % of DRAM peak -- latency bound; unrolling lets the loads of the next digits issue under the current products
-#pragma unroll 3
+        // ncu (profiles/r02_ncu_lintrans_summary.csv): DRAM traffic = decomposition once + key once per group + outputs (the gather costs no extra
+        // sectors), 38 % of DRAM peak. Unrolling this loop by 3 (78 -> 64 registers under launch bounds) measured 11 % SLOWER: kept rolled.
         for (int d = 0; d < p.nd; d++) {
             const u64 e0 = __ldg(p.evk + (size_t)d * p.e_ds + erow), e1 = __ldg(p.evk + (size_t)d * p.e_ds + p.e_cs + erow);
             const u64* x = p.decomp + (size_t)d * p.d_ds + drow;
