@@ -245,14 +245,19 @@ int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64
     const size_t N = c.N, nq = level + 1, nqo = nq - nb_rescales;
     const size_t in_words = 2 * nq * N, out_words = 2 * nqo * N;
     LGPU_CUDA_OK(cudaSetDevice(c.device));
-    // Two independent streams, each doing H2D -> compute -> D2H for alternating chunks: the copies of one chunk overlap
-    // the compute of the other (copy engines run concurrently with the SMs). Streams and staging buffers live in the
+    // Independent streams, each doing H2D -> compute -> D2H for every kStreams-th chunk: the copies of one chunk overlap the compute of the
+    // others (copy engines run concurrently with the SMs). Streams and staging buffers live in the
     // context; one host-pipeline call at a time per context.
     Ctx::HostPipe& hp = ctx->c.host_pipe;
     std::lock_guard<std::mutex> lock(hp.mu);
     int rc = 0;
     const size_t need[3] = {chunk * in_words, chunk * in_words, chunk * out_words};
-    for (int i = 0; i < 2 && !rc; i++) {
+    constexpr int NS = Ctx::HostPipe::kStreams;
+    // two streams by default: a third (LGPU_HOST_STREAMS=3) measured 531 vs 548 ct/s -- the H2D engine is already busy back to back at the
+    // ~50 GB/s this link sustains while the downloads run the other way
+    static const int ns_env = [] { const char* e = getenv("LGPU_HOST_STREAMS"); int v = e ? atoi(e) : 2; return v >= 1 && v <= NS ? v : 2; }();
+    const int ns = ns_env;
+    for (int i = 0; i < ns && !rc; i++) {
         if (!hp.st[i] && cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking) != cudaSuccess) rc = -1;
         for (int k = 0; k < 3 && !rc; k++) {
             if (hp.buf[i][k] && hp.cap[k] >= need[k]) continue;
@@ -263,20 +268,20 @@ int lgpu_ckks_mulrelin_rescale_batch_host(lgpu_ctx* ctx, int level, const uint64
     if (rc) lgpu::set_error("allocation failed in mulrelin_rescale_batch_host");
     else for (int k = 0; k < 3; k++) hp.cap[k] = std::max(hp.cap[k], need[k]);
     cudaStream_t* st = hp.st;
-    u64 *dA[2] = {hp.buf[0][0], hp.buf[1][0]}, *dB[2] = {hp.buf[0][1], hp.buf[1][1]}, *dO[2] = {hp.buf[0][2], hp.buf[1][2]};
-    for (int k = 0, i = 0; !rc && k < batch; k += chunk, i ^= 1) {
+    for (int k = 0, i = 0; !rc && k < batch; k += chunk, i = (i + 1) % ns) {
         const int nb = std::min(chunk, batch - k);
-        if (cudaMemcpyAsync(dA[i], ct_a_host + (size_t)k * in_words, nb * in_words * 8, cudaMemcpyHostToDevice, st[i]) != cudaSuccess ||
-            cudaMemcpyAsync(dB[i], ct_b_host + (size_t)k * in_words, nb * in_words * 8, cudaMemcpyHostToDevice, st[i]) != cudaSuccess) {
+        u64 *dA = hp.buf[i][0], *dB = hp.buf[i][1], *dO = hp.buf[i][2];
+        if (cudaMemcpyAsync(dA, ct_a_host + (size_t)k * in_words, nb * in_words * 8, cudaMemcpyHostToDevice, st[i]) != cudaSuccess ||
+            cudaMemcpyAsync(dB, ct_b_host + (size_t)k * in_words, nb * in_words * 8, cudaMemcpyHostToDevice, st[i]) != cudaSuccess) {
             lgpu::set_error("H2D copy failed"); rc = -1; break;
         }
-        rc = ckks_mulrelin_rescale(&c, level, dA[i], dB[i], g, nb_rescales, dO[i], nb, st[i]);
+        rc = ckks_mulrelin_rescale(&c, level, dA, dB, g, nb_rescales, dO, nb, st[i]);
         if (rc) break;
-        if (cudaMemcpyAsync(ct_out_host + (size_t)k * out_words, dO[i], nb * out_words * 8, cudaMemcpyDeviceToHost, st[i]) != cudaSuccess) {
+        if (cudaMemcpyAsync(ct_out_host + (size_t)k * out_words, dO, nb * out_words * 8, cudaMemcpyDeviceToHost, st[i]) != cudaSuccess) {
             lgpu::set_error("D2H copy failed"); rc = -1; break;
         }
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ns; i++) {
         if (st[i]) cudaStreamSynchronize(st[i]);
     }
     if (!rc) {

@@ -103,8 +103,9 @@ struct Ctx {
     // staging state of the *_host entry points, created on first use and kept for the life of the context (allocating
     // and freeing ~2 GB of device staging per call was a visible, noisy part of the end-to-end time)
     struct HostPipe {
-        cudaStream_t st[2] = {nullptr, nullptr};
-        u64* buf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [stream][A, B, out]
+        static constexpr int kStreams = 3;   // capacity; two are used by default (capi2.cu)
+        cudaStream_t st[kStreams] = {nullptr, nullptr, nullptr};
+        u64* buf[kStreams][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [stream][A, B, out]
         size_t cap[3] = {0, 0, 0};                                                       // words per buffer kind
         std::mutex mu;                                                                   // one host-pipeline call at a time PER CONTEXT (contexts on other GPUs run concurrently)
     } host_pipe;

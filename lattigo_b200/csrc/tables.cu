@@ -375,7 +375,7 @@ void destroy_context(Ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto& kv : c->auto_index) cudaFree(kv.second);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < Ctx::HostPipe::kStreams; i++) {
         if (c->host_pipe.st[i]) { cudaStreamSynchronize(c->host_pipe.st[i]); cudaStreamDestroy(c->host_pipe.st[i]); }
         for (int k = 0; k < 3; k++) cudaFree(c->host_pipe.buf[i][k]);
     }
