@@ -34,7 +34,7 @@ int lgpu_lintrans_evaluate_many(lgpu_ctx* ctx, int level_in, const uint64_t* ct_
     REQUIRE_ALIGNED(AL(ct_in));
     GaloisKeySet ks;
     if (gks) {
-        REQUIRE(gks->n_keys == 0 || (gks->gal_els && gks->keys), "null Galois key arrays");
+        REQUIRE(gks->n_keys >= 0 && (gks->n_keys == 0 || (gks->gal_els && gks->keys)), "null Galois key arrays");
         ks.n = gks->n_keys; ks.gal_els = (const u64*)gks->gal_els;
         ks.keys.resize(ks.n);
         for (int i = 0; i < ks.n; i++) {
@@ -106,6 +106,7 @@ int lgpu_blind_rotate_core(lgpu_ctx* ctx, const uint64_t* a_host, int n_lwe, uin
         sets[has[ai] ? dlog[ai] : 0].push_back(i);
     }
     GaloisKeySet ks;
+    REQUIRE(gks->n_keys >= 0 && (gks->n_keys == 0 || (gks->gal_els && gks->keys)), "null Galois key arrays");
     ks.n = gks->n_keys; ks.gal_els = (const u64*)gks->gal_els;
     ks.keys.resize(ks.n);
     for (int i = 0; i < ks.n; i++) if (to_gct3(&gks->keys[i], ks.keys[i])) return -1;
@@ -155,6 +156,7 @@ int lgpu_evaluator_automorphism_hoisted_lazy(lgpu_ctx* ctx, int level_q, const u
                                              uint64_t* out1p, int batch, size_t stride_ct, size_t stride_q, size_t stride_p, void* stream) {
     REQUIRE_DEVICE(ctx);
     REQUIRE(ct0 && decomp && out0q && out0p && out1q && out1p, "null polynomial");
+    REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
     REQUIRE_ALIGNED(AL(ct0) && AL(decomp) && AL(out0q) && AL(out0p) && AL(out1q) && AL(out1p) && ((stride_ct | stride_q | stride_p) & 1) == 0);
     GadgetCt g;
     if (to_gct3(gk, g)) return -1;

@@ -255,6 +255,9 @@ int gen_evaluation_key(const Ctx* c, int pw2, const u64* sk_in, const u64* sk_ou
     const int nd = levelP >= 0 ? base_rns_decomposition_vector_size(levelQ, levelP) : levelQ + 1;
     if (n_digits != nd) { set_error("evaluation key: n_digits != BaseRNSDecompositionVectorSize(levelQ, levelP)"); return -1; }
     if (n_pw2_max < 1 || n_pw2_max > 64) { set_error("evaluation key: n_pw2_max out of [1, 64]"); return -1; }
+    if (pw2 < 0 || pw2 > 62) { set_error("evaluation key: BaseTwoDecomposition out of [0, 62]"); return -1; }
+    for (int i = 0; pw2_sizes && i < n_digits; i++)
+        if (pw2_sizes[i] < 1 || pw2_sizes[i] > n_pw2_max) { set_error("evaluation key: pw2_sizes[i] out of [1, n_pw2_max]"); return -1; }
     const int entries = n_digits * n_pw2_max;
     const size_t ebs = 2 * rows * N;
     if (encrypt_zero_sk(c, levelQ, levelP, sk_out, evk + rows * N, ebs, e, evk, ebs, true, true, entries, st)) return -1;
@@ -332,7 +335,7 @@ int lgpu_sample_gaussian(lgpu_ctx* ctx, double sigma, double bound, uint64_t see
 int lgpu_small_poly_to_rns(lgpu_ctx* ctx, int level_q, int level_p, const int64_t* small, uint64_t* out_q, uint64_t* out_p, int batch, size_t stride_q,
                            size_t stride_p, void* stream) {
     REQUIRE_DEVICE(ctx);
-    REQUIRE(small && (out_q || out_p) && batch >= 1, "bad argument");
+    REQUIRE(small && (out_q || out_p) && batch >= 1 && batch <= 65535, "bad argument");
     const Ctx& c = ctx->c;
     RowMap rm;
     if (out_q) {
