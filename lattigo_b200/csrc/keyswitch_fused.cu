@@ -54,6 +54,11 @@ static SideStream* side_stream(int device) {
 // Measured: evaluating the basis extension on the FP64 pipe (fp_src == 2) makes K2 ~25 % slower than the 128-bit integer
 // MAC, because the FP64 pipe then carries both the extension and the butterflies while the integer pipes idle.
 // Kept selectable for experiments (LGPU_K2_FPSUM=1).
+// LGPU_K2_SPLIT: 23-bit-halves basis extension (ks_ext_split) on the FP64 target rows of digits whose sources are all FP64-pipe primes
+static int k2_split() {
+    static const int v = [] { const char* e = getenv("LGPU_K2_SPLIT"); return e ? atoi(e) : 0; }();
+    return v;
+}
 static int k2_fpsum() {
     static const int on = [] { const char* e = getenv("LGPU_K2_FPSUM"); return e && atoi(e) ? 1 : 0; }();
     return on;
@@ -134,6 +139,7 @@ struct KsStridedParams {
     int skip_own;     // 1: rows that belong to the digit itself are skipped (key-switch); 0: every launch row is a target
     int single_rule;  // see KsPrepParams
     int src_limb0;    // global limb of source row 0 (single-limb rule only)
+    int split23;      // 1: full digits whose sources are all FP64-pipe primes take ks_ext_split on the FP64 target rows (LGPU_K2_SPLIT)
     // PRO_BCAST (rescale): e = cred(bc[x] + bc_add, bc_q) + s0[launch row]
     const u64* bc; size_t bc_bs; u64 bc_add, bc_q;
     u64 s0[kMaxRows];
@@ -152,6 +158,37 @@ __device__ __forceinline__ u64 ks_ext(const u64 (&y)[NSMAX], int nS, int v, cons
     const u64 hhi = mulhi64(rlo * qinv, q);
     u64 r = rhi - hhi + q + vt[v];
     return cred(r + q - half_t, q);
+}
+
+// The same residue when every source prime of the digit AND the target prime are FP64-pipe primes (below 2^46.3), as a lazy double in
+// (-0.66q, 0.66q) for the FP64 butterflies that follow. With 23-bit halves y = y0 + y1 2^23, c = c0 + c1 2^23 and c' = c 2^23 mod q = d0 + d1 2^23:
+//   sum_i y_i c_i  ==  A + B 2^23 (mod q),   A = sum_i (y0 c0 + y1 d0),   B = sum_i (y0 c1 + y1 d1),
+// every partial product is below 2^48 and both sums over up to 6 sources stay below 2^51, so the 4 products per source are 32 x 32 -> 64 bit
+// multiply-adds without carry chains, and the reduction  A + (B 2^23 mod q) + (vt[v] - half_t)  takes 9 FP64 instructions (B 2^23 < 2^74 is an
+// exact double, so one fp_reduce brings it below q/2; the 2^52 biases of the integer -> double conversions are folded into the constants)
+// instead of a 128-bit Montgomery step plus 64-bit additions on the ALU pipe. `y` holds the two halves of a source word in its 32-bit halves
+// (packed when the tile is staged); c (plain, not Montgomery: KsDigit::off_cp) and c' are split the same way. vtb = vt[v] - half_t - 2^52.
+__device__ __forceinline__ u64 mad_wide(u32 a, u32 b, u64 c) {
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+template <int NSMAX>
+__device__ __forceinline__ double ks_ext_split(const u64 (&y)[NSMAX], const u32 (&c0)[NSMAX], const u32 (&c1)[NSMAX], const u32 (&d0)[NSMAX],
+                                               const u32 (&d1)[NSMAX], double vtb, double fq, double fqinv) {
+    u64 A = 0, B = 0;
+#pragma unroll
+    for (int i = 0; i < NSMAX; i++) {
+        const u32 y0 = (u32)y[i], y1 = (u32)(y[i] >> 32);
+        A = mad_wide(y0, c0[i], A);
+        A = mad_wide(y1, d0[i], A);
+        B = mad_wide(y0, c1[i], B);
+        B = mad_wide(y1, d1[i], B);
+    }
+    const double ab = __longlong_as_double((long long)(A | 0x4330000000000000ull));                 // 2^52 + A
+    const double bb = __longlong_as_double((long long)(B | 0x4330000000000000ull));                 // 2^52 + B
+    const double t = fp_reduce(__fma_rn(bb, 8388608.0, -37778931862957161709568.0), fq, fqinv);     // (2^52 + B) 2^23 - 2^75 = B 2^23, exact
+    return fp_reduce(__dadd_rn(__dadd_rn(ab, vtb), t), fq, fqinv);                                  // (2^52 + A) + (vt - half_t - 2^52), exact
 }
 
 enum { PRO_MODUP = 0, PRO_BCAST = 1 };
@@ -332,6 +369,8 @@ __global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(
     unsigned char* s_v = reinterpret_cast<unsigned char*>(dsm + NSMAX * R * LB);   // [R][LB]
     __shared__ u64 s_c[J][NSMAX];
     __shared__ u64 s_vt[J][NSMAX + 1];
+    __shared__ u64 s_c2[FP ? J : 1][NSMAX];              // split path: c 2^23 mod q
+    __shared__ double s_vtd[FP ? J : 1][NSMAX + 1];      // split path: vt[v] - half_t - 2^52
     const int tid = threadIdx.x, lx = tid % LB, jj = tid / LB;
     const int jrow = blockIdx.y * J + jj;
     const bool valid = jrow < p.rm.nrows;
@@ -346,17 +385,33 @@ __global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(
     const int l0 = blockIdx.x * LB;
     const u64* Y = p.Y + (size_t)b * p.y_bs + (size_t)r0 * N;
     const unsigned char* V = p.V + (size_t)b * p.v_bs + (size_t)d * N;
+    const bool split = FP && p.split23 && dg.fp_src != 0 && nS == NSMAX;      // CTA-uniform
     for (int idx = tid; idx < nS * R * LB; idx += 256) {
         const int i = idx / (R * LB), k = (idx / LB) % R, x = idx % LB;
-        s_y[idx] = Y[(size_t)i * N + k * stride + l0 + x];
+        u64 w = Y[(size_t)i * N + k * stride + l0 + x];
+        if (split) w = (w & 0x7FFFFFull) | ((w >> 23) << 32);                  // 23-bit halves for ks_ext_split (w < 2^46.3)
+        s_y[idx] = w;
     }
     for (int idx = tid; idx < R * LB / 4; idx += 256) {      // 4 bytes per thread: 16-column groups are 4-byte aligned
         const int k = (idx * 4) / LB, x = (idx * 4) % LB;
         reinterpret_cast<unsigned int*>(s_v)[idx] = *reinterpret_cast<const unsigned int*>(V + k * stride + l0 + x);
     }
     if (valid) {
-        if (lx < nS) s_c[jj][lx] = p.blob[dg.off_c + (size_t)limb * dg.ldc + lx];
-        if (lx <= nS) s_vt[jj][lx] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + lx];
+        if (split) {
+            // plain constants c, c' = c 2^23 mod q and the double table vt[v] - half_t of this target row
+            const double fq = p.limbs[limb].fq, fqinv = p.limbs[limb].fqinv;
+            if (lx < nS) {
+                const u64 cp = p.blob[dg.off_cp + (size_t)limb * dg.ldc + lx];
+                const double w = u2d(fp_canon(8388608.0, fq, fqinv));
+                s_c[jj][lx] = cp;
+                s_c2[jj][lx] = fp_canon(fp_mulmod(u2d(cp), w, fq, fqinv), fq, fqinv);
+            }
+            if (lx <= nS)
+                s_vtd[jj][lx] = __dadd_rn(__dadd_rn(u2d(p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + lx]), -u2d(p.blob[dg.off_half_t + limb])), -FP_TWO52);
+        } else {
+            if (lx < nS) s_c[jj][lx] = p.blob[dg.off_c + (size_t)limb * dg.ldc + lx];
+            if (lx <= nS) s_vt[jj][lx] = p.blob[dg.off_vt + (size_t)limb * (dg.ldc + 1) + lx];
+        }
     }
     __syncthreads();
     if (!valid) return;
@@ -367,6 +422,39 @@ __global__ void __launch_bounds__(256, KS_STRIDED_J4_MINB) ks_strided_j4_kernel(
     const int l = l0 + lx;
     u64* out = p.P1 + (size_t)b * p.p1_bs + (size_t)d * p.p1_ds + (size_t)row * N + l;
     u64 e[R];
+    if constexpr (FP) {
+        if (split) {
+            const double fq = L.fq, fqinv = L.fqinv;
+            const double* tw = L.ftw_fwd;
+            u32 c0[NSMAX], c1[NSMAX], d0[NSMAX], d1[NSMAX];
+#pragma unroll
+            for (int i = 0; i < NSMAX; i++) {
+                const u64 cw = s_c[jj][i], dw = s_c2[jj][i];
+                c0[i] = (u32)cw & 0x7FFFFFu; c1[i] = (u32)(cw >> 23);
+                d0[i] = (u32)dw & 0x7FFFFFu; d1[i] = (u32)(dw >> 23);
+            }
+            double x[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                u64 y[NSMAX];
+#pragma unroll
+                for (int i = 0; i < NSMAX; i++) y[i] = s_y[(i * R + k) * LB + lx];
+                x[k] = ks_ext_split<NSMAX>(y, c0, c1, d0, d1, s_vtd[jj][s_v[k * LB + lx]], fq, fqinv);
+            }
+#pragma unroll
+            for (int u = 0; u < RL; u++) {
+                const int half = 1 << (RL - 1 - u);
+#pragma unroll
+                for (int k = 0; k < R; k++) {
+                    if (k & half) continue;
+                    fp_fwd_bfly(x[k], x[k + half], __ldg(tw + (1 << u) + (k >> (RL - u))), fq, fqinv);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < R; k++) out[(size_t)k * stride] = (u64)__double_as_longlong(x[k]);
+            return;
+        }
+    }
     if (KS_FULL && nS == NSMAX) {          // full digit (every digit but possibly the last): no per-source predication
 #pragma unroll
         for (int k = 0; k < R; k++) {
@@ -620,13 +708,23 @@ __device__ __forceinline__ ulonglong2 ldg128(const u64* p) {
     return KS_STREAM ? __ldcs(reinterpret_cast<const ulonglong2*>(p)) : __ldg(reinterpret_cast<const ulonglong2*>(p));
 }
 
+// MACV selects the pipe of the multiply-accumulate (LGPU_K3_VARIANT = 10 + MACV):
+//   0  integer pipes: MRedLazy(key, x) with the biased-integer x, u64 sums, one Barrett step at the end;
+//   1  FP64 pipe: acc += fp_mulmod(x, double(key)) with x left as the double the last round produced -- 8 FP64 instructions per term instead of
+//      ~21 integer ones. The key is in Montgomery form (key * 2^64), so the sum carries a factor 2^64 that one fp_mulmod by 2^-64 mod q removes
+//      per output coefficient; |acc| <= kMaxDigits * q < 2^52 stays an exact integer. Key / own-row words at or above 2^46 (never produced by the
+//      reference: both are canonical residues) are Barrett-reduced first;
+//   2  component 0 as in 1, component 1 as in 0 (both pipes busy in the MAC phase).
+template <int MACV>
 __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams p) {
     constexpr int CL = 12, T = 512;
+    constexpr bool F0 = MACV >= 1, F1 = MACV == 1;
     extern __shared__ u64 smem[];
     __shared__ __align__(8) u64 s_bar;
     double* fsm = reinterpret_cast<double*>(smem);
     // accumulators: component c, pair j (coefficients 8*tid + 2j, 2j+1) at acc + ((c*4 + j) * T + tid) * 2
     ulonglong2* accs = reinterpret_cast<ulonglong2*>(smem + 4096);       // the transform tile is XOR-swizzled, not padded
+    double2* accd = reinterpret_cast<double2*>(smem + 4096);
     const int b = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
     const int limb = p.rm.limb[blockIdx.z];
     const int row = p.rm.drow[blockIdx.z];
@@ -654,6 +752,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
         int dn = d + 1;
         if (dn == own_d) dn++;
         u64 xv[8];
+        double xd[8];
         if (!own) {
             {
                 double x[8];
@@ -694,45 +793,97 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                 tok = mbar_arrive(bar);
                 pending = true;
                 fp8_bflys(x, t, fq, fqinv);
+                if (!F1) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) xv[k] = KS_LAZY_X ? fp_biased_u64(x[k], off52) : fp_canon(x[k], fq, fqinv);
+                    for (int k = 0; k < 8; k++) xv[k] = KS_LAZY_X ? fp_biased_u64(x[k], off52) : fp_canon(x[k], fq, fqinv);
+                }
+                if (F0) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) xd[k] = x[k];
+                }
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) { const ulonglong2 v = ldg128(xin + 2 * j); xv[2 * j] = v.x; xv[2 * j + 1] = v.y; }
+            if (F0) {
+                if ((xv[0] | xv[1] | xv[2] | xv[3] | xv[4] | xv[5] | xv[6] | xv[7]) >> 46) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) xv[k] = bred_add(xv[k], q, L.bred_hi);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) xd[k] = u2d(xv[k]);
+            }
         }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             ulonglong2 k0[2], k1[2];
 #pragma unroll
             for (int j = 0; j < 2; j++) { k0[j] = ldg128(e0 + 4 * h + 2 * j); k1[j] = ldg128(e1 + 4 * h + 2 * j); }
+            if (F0) {
+                u64 g = k0[0].x | k0[0].y | k0[1].x | k0[1].y;
+                if (F1) g |= k1[0].x | k1[0].y | k1[1].x | k1[1].y;
+                if (g >> 46) {
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        k0[j].x = bred_add(k0[j].x, q, L.bred_hi); k0[j].y = bred_add(k0[j].y, q, L.bred_hi);
+                        if (F1) { k1[j].x = bred_add(k1[j].x, q, L.bred_hi); k1[j].y = bred_add(k1[j].y, q, L.bred_hi); }
+                    }
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const int pj = 2 * h + j;
-                const u64 xa = xv[2 * pj], xb = xv[2 * pj + 1];
-                ulonglong2 m0, m1;
-                m0.x = mred_lazy(k0[j].x, xa, q, qinv); m0.y = mred_lazy(k0[j].y, xb, q, qinv);
-                m1.x = mred_lazy(k1[j].x, xa, q, qinv); m1.y = mred_lazy(k1[j].y, xb, q, qinv);
-                ulonglong2* A0 = accs + (size_t)(0 * 4 + pj) * T + tid;
-                ulonglong2* A1 = accs + (size_t)(1 * 4 + pj) * T + tid;
-                if (d != 0) {
+                if (F0) {
+                    double2 m0;
+                    m0.x = fp_mulmod(xd[2 * pj], u2d(k0[j].x), fq, fqinv); m0.y = fp_mulmod(xd[2 * pj + 1], u2d(k0[j].y), fq, fqinv);
+                    double2* A0 = accd + (size_t)(0 * 4 + pj) * T + tid;
+                    if (d != 0) { const double2 c0 = *A0; m0.x = __dadd_rn(m0.x, c0.x); m0.y = __dadd_rn(m0.y, c0.y); }
+                    *A0 = m0;
+                } else {
+                    ulonglong2 m0;
+                    m0.x = mred_lazy(k0[j].x, xv[2 * pj], q, qinv); m0.y = mred_lazy(k0[j].y, xv[2 * pj + 1], q, qinv);
+                    ulonglong2* A0 = accs + (size_t)(0 * 4 + pj) * T + tid;
                     // plain adds: every term is < 2q < 2^47 and there are at most kMaxDigits of them, so the u64 sums cannot
                     // overflow; one Barrett step in the epilogue gives the canonical residue the reference's Reduce leaves
-                    const ulonglong2 c0 = *A0, c1 = *A1;
-                    m0.x += c0.x; m0.y += c0.y; m1.x += c1.x; m1.y += c1.y;
+                    if (d != 0) { const ulonglong2 c0 = *A0; m0.x += c0.x; m0.y += c0.y; }
+                    *A0 = m0;
                 }
-                *A0 = m0; *A1 = m1;
+                if (F1) {
+                    double2 m1;
+                    m1.x = fp_mulmod(xd[2 * pj], u2d(k1[j].x), fq, fqinv); m1.y = fp_mulmod(xd[2 * pj + 1], u2d(k1[j].y), fq, fqinv);
+                    double2* A1 = accd + (size_t)(1 * 4 + pj) * T + tid;
+                    if (d != 0) { const double2 c1 = *A1; m1.x = __dadd_rn(m1.x, c1.x); m1.y = __dadd_rn(m1.y, c1.y); }
+                    *A1 = m1;
+                } else {
+                    ulonglong2 m1;
+                    m1.x = mred_lazy(k1[j].x, xv[2 * pj], q, qinv); m1.y = mred_lazy(k1[j].y, xv[2 * pj + 1], q, qinv);
+                    ulonglong2* A1 = accs + (size_t)(1 * 4 + pj) * T + tid;
+                    if (d != 0) { const ulonglong2 c1 = *A1; m1.x += c1.x; m1.y += c1.y; }
+                    *A1 = m1;
+                }
             }
         }
     }
     u64* o0 = p.acc + (size_t)b * p.acc_bs + (size_t)row * N + ((size_t)chunk << CL) + 8 * tid;
     u64* o1 = o0 + p.acc_cs;
+    const double rinv = u2d(mred(1, 1, q, qinv));      // 2^-64 mod q: takes the Montgomery factor of the key out of the FP64 sums
 #pragma unroll
     for (int pj = 0; pj < 4; pj++) {
-        const ulonglong2 c0 = accs[(size_t)(0 * 4 + pj) * T + tid], c1 = accs[(size_t)(1 * 4 + pj) * T + tid];
         ulonglong2 r0, r1;
-        r0.x = bred_add(c0.x, q, L.bred_hi); r0.y = bred_add(c0.y, q, L.bred_hi);
-        r1.x = bred_add(c1.x, q, L.bred_hi); r1.y = bred_add(c1.y, q, L.bred_hi);
+        if (F0) {
+            const double2 c0 = accd[(size_t)(0 * 4 + pj) * T + tid];
+            r0.x = fp_canon(fp_mulmod(c0.x, rinv, fq, fqinv), fq, fqinv); r0.y = fp_canon(fp_mulmod(c0.y, rinv, fq, fqinv), fq, fqinv);
+        } else {
+            const ulonglong2 c0 = accs[(size_t)(0 * 4 + pj) * T + tid];
+            r0.x = bred_add(c0.x, q, L.bred_hi); r0.y = bred_add(c0.y, q, L.bred_hi);
+        }
+        if (F1) {
+            const double2 c1 = accd[(size_t)(1 * 4 + pj) * T + tid];
+            r1.x = fp_canon(fp_mulmod(c1.x, rinv, fq, fqinv), fq, fqinv); r1.y = fp_canon(fp_mulmod(c1.y, rinv, fq, fqinv), fq, fqinv);
+        } else {
+            const ulonglong2 c1 = accs[(size_t)(1 * 4 + pj) * T + tid];
+            r1.x = bred_add(c1.x, q, L.bred_hi); r1.y = bred_add(c1.y, q, L.bred_hi);
+        }
         *reinterpret_cast<ulonglong2*>(o0 + 2 * pj) = r0;
         *reinterpret_cast<ulonglong2*>(o1 + 2 * pj) = r1;
     }
@@ -965,7 +1116,7 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
     // ---- K2 + K3: FP64 rows on `st`, integer rows on the side stream
     sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.Y = Y; sp.y_bs = (size_t)nq * N; sp.V = V; sp.v_bs = (size_t)nd * N;
     sp.P1 = P1; sp.p1_ds = (size_t)nrows * N; sp.p1_bs = (size_t)nd * nrows * N;
-    sp.logN = c->logN; sp.nq = nq; sp.k = k; sp.nd = nd; sp.skip_own = 1; sp.single_rule = 1; sp.src_limb0 = 0;
+    sp.logN = c->logN; sp.nq = nq; sp.k = k; sp.nd = nd; sp.skip_own = 1; sp.single_rule = 1; sp.src_limb0 = 0; sp.split23 = k2_split();
     KsChunkParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.limbs = c->d_limbs; cp.P1 = P1; cp.p1_ds = sp.p1_ds; cp.p1_bs = sp.p1_bs;
@@ -1014,9 +1165,15 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * fp.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
         // LGPU_K3_VARIANT=0 selects the 256 x 16 shared-memory-MAC kernel (kept as the cross-check of the default one)
         static const int k3v = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 10; }();
-        if (k3v != 0) {
-            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ks_chunk_mac_fp8r_kernel<<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        if (k3v == 11) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8r_kernel<1><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        } else if (k3v == 12) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8r_kernel<2><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        } else if (k3v != 0) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8r_kernel<0><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
         } else {
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ks_chunk_mac_kernel<true><<<dim3(batch, chunks, fp.nrows), 256, smem, st>>>(cp);
@@ -1320,7 +1477,7 @@ int moddown_ntt_fused(const Ctx* c, int levelQ, int levelP, const u64* acc, size
     memset(&sp, 0, sizeof(sp));
     sp.limbs = c->d_limbs; sp.blob = c->d_blob; sp.Y = Y; sp.y_bs = (size_t)np * N; sp.V = V; sp.v_bs = N;
     sp.P1 = P1; sp.p1_ds = (size_t)nq * N; sp.p1_bs = (size_t)nq * N;
-    sp.logN = c->logN; sp.nq = nq; sp.k = np; sp.nd = 1; sp.skip_own = 0; sp.single_rule = 0; sp.src_limb0 = c->nQ;
+    sp.logN = c->logN; sp.nq = nq; sp.k = np; sp.nd = 1; sp.skip_own = 0; sp.single_rule = 0; sp.src_limb0 = c->nQ; sp.split23 = k2_split();
     sp.dg[0].nS = (unsigned short)np; sp.dg[0].ldc = (unsigned short)m.nS;
     sp.dg[0].off_c = (unsigned)m.off_qoverqimodp; sp.dg[0].off_vt = (unsigned)m.off_vtimesqmodp; sp.dg[0].off_half_t = (unsigned)m.off_half_t;
     sp.dg[0].off_cp = (unsigned)m.off_c_plain;

@@ -350,6 +350,56 @@ struct FpFwdOps2 : FpFwdOps<RL, 0> {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+// forward FP64, register copy-out (LGPU_NTT_PERSIST_V=5, A/B): after round 4 every thread holds 8 CONSECUTIVE canonical coefficients, so they go
+// straight to global memory as four 128-bit stores (64 contiguous bytes per thread, as in the key-switch MAC kernel) instead of being written
+// back to the tile, exchanged inside the warp and copied out 8 bytes at a time: 8 STS + 8 LDS + a warp barrier + 4 STG less per thread and tile.
+// Needs 16-byte aligned output rows (the dispatcher checks and falls back to FpFwdOps2).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int RL>
+struct FpFwdOps3 : FpFwdOps2<RL> {
+    static constexpr int T = 512;
+    static constexpr size_t kSmem = (size_t)4096 * sizeof(u64);
+
+    static __device__ __forceinline__ void pass2(const PersistParams& p, int lt, int chunk, u64* smem) {
+        constexpr int s1 = RL;
+        const int tid = threadIdx.x;
+        const TileRef t = tile_ref(p, lt);
+        const LimbConst& L = p.limbs[t.limb];
+        u64* io = t.out + ((size_t)chunk << 12);
+        FpFwdOps2<RL>::template round1<0>(L, io, smem, chunk, tid);
+        __syncthreads();
+        double* fsm = reinterpret_cast<double*>(smem);
+        const double fq = L.fq, fqinv = L.fqinv;
+        const double* tw = L.ftw_fwd;
+        double tt[7];
+        fp8_load_tw<3>(tt, tw, s1, chunk, tid);
+        fp8s_round2(fsm, tt, fq, fqinv, tid);              // stages 3..5
+        fp8_load_tw<6>(tt, tw, s1, chunk, tid);
+        fp8s_pair_sync(tid);
+        fp8s_round3(fsm, tt, fq, fqinv, tid);              // stages 6..8
+        fp8_load_tw<9>(tt, tw, s1, chunk, tid);
+        __syncwarp();
+        double x[8];
+        fp8s_load_r4(fsm, x, tid);
+        fp8_bflys(x, tt, fq, fqinv);                       // stages 9..11
+        u64* g = io + 8 * tid;
+        if (t.mul) {
+            const u64* mu = t.mul + ((size_t)chunk << 12) + 8 * tid;
+            const u64 q = L.q, qinv = L.qinv;
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                const ulonglong2 m = __ldg(reinterpret_cast<const ulonglong2*>(mu + k));
+                *reinterpret_cast<ulonglong2*>(g + k) = make_ulonglong2(mred(fp_canon(x[k], fq, fqinv), m.x, q, qinv), mred(fp_canon(x[k + 1], fq, fqinv), m.y, q, qinv));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k += 2)
+                *reinterpret_cast<ulonglong2*>(g + k) = make_ulonglong2(fp_canon(x[k], fq, fqinv), fp_canon(x[k + 1], fq, fqinv));
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
 // inverse, FP64-pipe primes: 256 threads x 16 elements (fp_inv_round). pass 1 = chunk stages (deepest first), raw
 // renormalised doubles out; pass 2 = strided stages with N^-1 folded into the last one, canonical output.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -859,6 +909,83 @@ static int persist_launch_tma(const Ctx* c, const RowMap& rm, CSpan in, Span out
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fourth-generation loop (LGPU_NTT_PERSIST_V=6, A/B), forward FP64 with the register copy-out: STATIC tile schedule (tile t belongs to CTA t mod grid;
+// every CTA of the persistent grid is resident and walks its tiles in increasing order, and a pass-2 tile only ever waits for tiles with smaller
+// numbers, so the smallest unfinished tile is never blocked) and a DOUBLE-BUFFERED tile: no ticket atomics, no ticket hand-over, and the only CTA
+// barrier left is the one after round 1 of a pass-2 tile (it also separates the two uses of a buffer, since every warp passes it between them).
+// Pass-1 tiles (registers only) publish per warp: __syncwarp, then lane 0 fences and bumps the limb-transform's counter (target n1 x warps).
+// ---------------------------------------------------------------------------------------------------------------------
+template <class Ops>
+__global__ void __launch_bounds__(Ops::T, Ops::MINB) ntt_persist3_kernel(PersistParams p) {
+    extern __shared__ u64 psm[];
+    const int per = p.n1 + p.n2;
+    const unsigned need = (unsigned)p.n1 * (Ops::T / 32);
+    int par = 0;
+    for (int t = blockIdx.x; t < p.total; t += gridDim.x) {
+        const int s = t / per, j = t - s * per;
+        if (j < p.n1) {
+            if (s < p.nLT) {
+                Ops::pass1(p, s, j, psm);
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) { __threadfence(); atomicAdd(p.ctr + 1 + s, 1u); }
+            }
+        } else {
+            const int lt = s - p.D;
+            if (lt >= 0) {
+                if ((threadIdx.x & 31) == 0) {
+                    const unsigned* c = p.ctr + 1 + lt;
+                    while (ld_acquire_u32(c) < need) __nanosleep(64);
+                }
+                __syncwarp();
+                Ops::pass2(p, lt, j - p.n1, psm + (par << 12));
+                par ^= 1;
+            }
+        }
+    }
+}
+
+template <class Ops>
+static int persist_launch3(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st, CSpan mul) {
+    static int occ = 0, sms = 0;
+    auto kern = ntt_persist3_kernel<Ops>;
+    const size_t smem = 2 * Ops::kSmem;
+    if (occ == 0) {
+        LGPU_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int o = 0;
+        LGPU_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, Ops::T, smem));
+        cudaDeviceProp prop;
+        LGPU_CUDA_OK(cudaGetDeviceProperties(&prop, c->device));
+        sms = prop.multiProcessorCount;
+        occ = o > 0 ? o : 1;
+    }
+    PersistParams p;
+    p.limbs = c->d_limbs; p.rm = rm; p.in = in.p; p.out = out.p;
+    p.in_rs = in.row_stride; p.in_bs = in.batch_stride; p.out_rs = out.row_stride; p.out_bs = out.batch_stride;
+    p.logN = c->logN; p.batch = batch; p.nLT = rm.nrows * batch;
+    p.mul = mul.p; p.mul_rs = mul.row_stride; p.mul_bs = mul.batch_stride;
+    p.n1 = Ops::kN1; p.n2 = Ops::kN2;
+    const int per = p.n1 + p.n2;
+    const long tiles = (long)p.nLT * per;
+    int grid = sms * occ;                       // never more than the resident CTAs: the static schedule relies on it
+    if ((long)grid > tiles) grid = (int)tiles;
+    static const int dmul = [] { const char* e = getenv("LGPU_NTT_PERSIST_D"); return e ? atoi(e) : 0; }();
+    int D = dmul > 0 ? dmul : (int)((5L * grid / 2 + per - 1) / per);
+    if (D < 1) D = 1;
+    p.D = D;
+    p.total = (p.nLT + D) * per;
+    unsigned* ctr = nullptr;
+    const size_t bytes = (size_t)(1 + p.nLT) * sizeof(unsigned);
+    LGPU_CUDA_OK(cudaMallocAsync((void**)&ctr, bytes, st));
+    LGPU_CUDA_OK(cudaMemsetAsync(ctr, 0, bytes, st));
+    p.ctr = ctr;
+    kern<<<grid, Ops::T, smem, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(ctr, st);
+    if (e != cudaSuccess) { set_error(std::string("ntt_persist3_kernel: ") + cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+
 template <class Ops, bool LOOP2 = false>
 static int persist_launch(const Ctx* c, const RowMap& rm, CSpan in, Span out, int batch, cudaStream_t st, CSpan mul) {
     static int occ = 0, sms = 0;
@@ -917,7 +1044,7 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
     static const int ph1int = [] { const char* e = getenv("LGPU_NTT_PH1INT"); return e ? atoi(e) : 0; }();
     // LGPU_NTT_PERSIST_V: 1 = first generation (padded tile, CTA barriers, serial ticket), 2 = first-generation tile code under
     // the claim-ahead loop, 3 (default) = swizzled tile + pair/warp syncs + claim-ahead loop, 4 = 3 + TMA bulk prefetch of the next chunk (measured
-    // 5 % slower than 3: profiles/r02_ntt_ab.json)
+    // 5 % slower than 3: profiles/r02_ntt_ab.json), 5 = 3 with the register copy-out (FpFwdOps3), 6 = 5 under the static-schedule / double-buffered loop
     static const int pv = [] { const char* e = getenv("LGPU_NTT_PERSIST_V"); return e ? atoi(e) : 3; }();
     // LGPU_NTT_PERSIST_IV: integer forward tile code, 3 (default) = 512 x 8 swizzled (IntFwdOps2), 2 = 256 x 16 padded (IntFwdOps)
     static const int piv = [] { const char* e = getenv("LGPU_NTT_PERSIST_IV"); return e ? atoi(e) : 3; }();
@@ -926,7 +1053,11 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
         if (kind == 0) {                                                                                                \
             if (inverse) return pv >= 2 ? persist_launch<FpInvOps<RLV>, true>(c, rm, in, out, batch, st, mul) : persist_launch<FpInvOps<RLV>>(c, rm, in, out, batch, st, mul);                               \
             if (ph1int) return persist_launch<FpFwdOps<RLV, 1>>(c, rm, in, out, batch, st, mul);                             \
-            if (pv >= 4) return persist_launch_tma<RLV>(c, rm, in, out, batch, st, mul);                                     \
+            if (pv == 4) return persist_launch_tma<RLV>(c, rm, in, out, batch, st, mul);                                     \
+            if (pv == 6 && aligned16(out.p) && even_words(out.row_stride, out.batch_stride) && (!mul.p || (aligned16(mul.p) && even_words(mul.row_stride, mul.batch_stride)))) \
+                return persist_launch3<FpFwdOps3<RLV>>(c, rm, in, out, batch, st, mul);                                      \
+            if (pv == 5 && aligned16(out.p) && even_words(out.row_stride, out.batch_stride) && (!mul.p || (aligned16(mul.p) && even_words(mul.row_stride, mul.batch_stride)))) \
+                return persist_launch<FpFwdOps3<RLV>, true>(c, rm, in, out, batch, st, mul);                                 \
             if (pv >= 3) return persist_launch<FpFwdOps2<RLV>, true>(c, rm, in, out, batch, st, mul);                        \
             if (pv == 2) return persist_launch<FpFwdOps<RLV, 0>, true>(c, rm, in, out, batch, st, mul);                      \
             return persist_launch<FpFwdOps<RLV, 0>>(c, rm, in, out, batch, st, mul);                                         \

@@ -20,8 +20,10 @@ VARIANTS = {
     "two_pass": {"LGPU_NTT_PERSIST": "0"},                                 # round-1 kernels: strided pass + chunk pass, 2 HBM round trips
     "persist_v1": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "1"},    # single HBM pass, padded tile, CTA barriers, serial ticket
     "persist_v2": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "2"},    # + claim-ahead tile loop
-    "persist_v3": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "3"},    # + swizzled tile, pair / warp level exchanges, hoisted addresses
-    "persist_v4": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "4"},    # + TMA bulk prefetch of the next chunk into a double-buffered tile (default)
+    "persist_v3": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "3"},    # + swizzled tile, pair / warp level exchanges, hoisted addresses (default)
+    "persist_v4": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "4"},    # v3 + TMA bulk prefetch of the next chunk into a double-buffered tile
+    "persist_v5": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "5"},    # v3 + register copy-out (128-bit stores straight from the last round)
+    "persist_v6": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PERSIST_V": "6"},    # v5 under a static tile schedule with a double-buffered tile (one CTA barrier per tile)
     "persist_ph1int": {"LGPU_NTT_PERSIST": "1", "LGPU_NTT_PH1INT": "1"},   # strided stages on the integer pipes (v1 tile code)
     "int_256x16": {"LGPU_NTT_PERSIST_IV": "2"},                            # integer rows: 256 x 16 padded tile (IntFwdOps) instead of the default 512 x 8 swizzled one
 }
