@@ -54,9 +54,10 @@ static SideStream* side_stream(int device) {
 // Measured: evaluating the basis extension on the FP64 pipe (fp_src == 2) makes K2 ~25 % slower than the 128-bit integer
 // MAC, because the FP64 pipe then carries both the extension and the butterflies while the integer pipes idle.
 // Kept selectable for experiments (LGPU_K2_FPSUM=1).
-// LGPU_K2_SPLIT: 23-bit-halves basis extension (ks_ext_split) on the FP64 target rows of digits whose sources are all FP64-pipe primes
+// LGPU_K2_SPLIT (default 1; 0 = the 128-bit Montgomery form everywhere): 23-bit-halves basis extension (ks_ext_split) on the FP64 target rows of
+// digits whose sources are all FP64-pipe primes. Measured on the headline step: K2 class 55.6 -> 52.2 ms per 4 steps (profiles/r02_ab_late.txt)
 static int k2_split() {
-    static const int v = [] { const char* e = getenv("LGPU_K2_SPLIT"); return e ? atoi(e) : 0; }();
+    static const int v = [] { const char* e = getenv("LGPU_K2_SPLIT"); return e ? atoi(e) : 1; }();
     return v;
 }
 static int k2_fpsum() {
@@ -1163,8 +1164,9 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         }
         // algorithmic bytes: P1 read once + accumulators written once + evk once per launch
         ProfScope ps(LGPU_KCLASS_MAC, st, 8.0 * N * fp.nrows * (batch * (double)(nd + 2) + 2.0 * nd), 1);
-        // LGPU_K3_VARIANT=0 selects the 256 x 16 shared-memory-MAC kernel (kept as the cross-check of the default one)
-        static const int k3v = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 10; }();
+        // LGPU_K3_VARIANT: 11 (default) = 512 x 8 kernel with the FP64-pipe MAC, 10 = integer-pipe MAC, 12 = one component each (measured 64.3 / 65.3 /
+        // 66.3 ms per 4 steps for the class, profiles/r02_ab_late.txt), 0 = the 256 x 16 shared-memory-MAC kernel (kept as a cross-check)
+        static const int k3v = [] { const char* e = getenv("LGPU_K3_VARIANT"); return e ? atoi(e) : 11; }();
         if (k3v == 11) {
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ks_chunk_mac_fp8r_kernel<1><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);

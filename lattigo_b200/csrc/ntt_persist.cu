@@ -1044,7 +1044,7 @@ int launch_ntt_persist(const Ctx* c, const RowMap& rm, bool inverse, int kind, C
     static const int ph1int = [] { const char* e = getenv("LGPU_NTT_PH1INT"); return e ? atoi(e) : 0; }();
     // LGPU_NTT_PERSIST_V: 1 = first generation (padded tile, CTA barriers, serial ticket), 2 = first-generation tile code under
     // the claim-ahead loop, 3 (default) = swizzled tile + pair/warp syncs + claim-ahead loop, 4 = 3 + TMA bulk prefetch of the next chunk (measured
-    // 5 % slower than 3: profiles/r02_ntt_ab.json), 5 = 3 with the register copy-out (FpFwdOps3), 6 = 5 under the static-schedule / double-buffered loop
+    // 5 % slower than 3: profiles/r02_ntt_ab.json), 5 = 3 with the register copy-out (FpFwdOps3; measured 0.600 vs 0.557 us per limb), 6 = 5 under the static-schedule / double-buffered loop (0.770): profiles/r02_ab_late.txt
     static const int pv = [] { const char* e = getenv("LGPU_NTT_PERSIST_V"); return e ? atoi(e) : 3; }();
     // LGPU_NTT_PERSIST_IV: integer forward tile code, 3 (default) = 512 x 8 swizzled (IntFwdOps2), 2 = 256 x 16 padded (IntFwdOps)
     static const int piv = [] { const char* e = getenv("LGPU_NTT_PERSIST_IV"); return e ? atoi(e) : 3; }();

@@ -248,6 +248,38 @@ def test_gadget_product_fused_pipeline_logn13():
     _gadget_case(lb, 14, q, p, 0, (4, 3), batch=3, seed=13)
 
 
+def test_gadget_product_fused_pipeline_lazy_key_words():
+    """Key words are canonical residues in the reference, but MRedLazy only needs their residue class: the FP64-pipe MAC of the fused pipeline
+    (K3, LGPU_K3_VARIANT=11) Barrett-reduces key words at or above 2^46 before converting them. Same product with key + m*q on the 45-bit rows."""
+    lb = _lb()
+    logN = 13
+    q, p = _mods(logN, [56, 45, 45, 45, 45, 45, 45], [55, 55, 55])
+    ctx = lb.Context(logN, q, p)
+    params = O.Parameters(logN, q, p)
+    N = params.N()
+    rng = np.random.default_rng(21)
+    ev_o = O.Evaluator(params); ev = lb.Evaluator(ctx)
+    evk_o = H.random_gadget_ciphertext(params, params.MaxLevelQ(), params.MaxLevelP(), rng)
+    lazy = evk_o.data.copy()                       # [digit][pw2][component][Q rows | P rows][N]
+    for r, qi in enumerate(q):
+        if qi < (1 << 46):
+            m = rng.integers(0, 1 << 16, size=lazy[..., r, :].shape, dtype=np.uint64)
+            m[..., ::3] = 0                        # a third of the words stay canonical: the guard is per group of words
+            lazy[..., r, :] += m * np.uint64(qi)
+    assert int(lazy.max()) >= 1 << 46
+    evk = lb.GadgetCiphertext(ctx, lazy, evk_o.LevelQ(), evk_o.LevelP(), 0, evk_o.pw2_sizes)
+    for levelQ in (6, 4):
+        batch = 2
+        cx = np.stack([H.rand_poly(q[: levelQ + 1], N, rng) for _ in range(batch)])
+        want = np.zeros((batch, 2, levelQ + 1, N), dtype=U64)
+        for b in range(batch):
+            ev_o.GadgetProduct(levelQ, cx[b].copy(), evk_o, [want[b, 0], want[b, 1]])
+        c0 = ctx.new_poly(levelQ + 1, batch); c1 = ctx.new_poly(levelQ + 1, batch)
+        ev.GadgetProduct(levelQ, ctx.to_device(cx), evk, c0, c1)
+        assert np.array_equal(ctx.to_host(c0), want[:, 0]) and np.array_equal(ctx.to_host(c1), want[:, 1]), levelQ
+    ctx.close()
+
+
 def test_gadget_product_single_p_and_bit_decomp():
     """core/rlwe/test_params.go:28-49: k = 1 with pw2 = 16; k = 0 (no P) with pw2 = 2; k = 1 without pw2."""
     lb = _lb()
