@@ -719,7 +719,7 @@ __device__ __forceinline__ ulonglong2 ldg128(const u64* p) {
 template <int MACV>
 __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams p) {
     constexpr int CL = 12, T = 512;
-    constexpr bool F0 = MACV >= 1, F1 = MACV == 1;
+    constexpr bool F0 = MACV >= 1, F1 = MACV == 1 || MACV == 3, R1 = MACV == 3;
     extern __shared__ u64 smem[];
     __shared__ __align__(8) u64 s_bar;
     double* fsm = reinterpret_cast<double*>(smem);
@@ -746,6 +746,7 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
     u64 raw[8];
     u64 tok = 0;
     bool pending = false;      // a tile read phase is outstanding: wait for it before overwriting the tile
+    double acc1[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};       // MACV == 3: component 1 accumulates in registers
     for (int d = 0; d < p.nd; d++) {
         const bool own = d == own_d;
         const u64* e0 = p.evk + (size_t)d * p.evk_ds + erow + 8 * tid;
@@ -849,7 +850,10 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                     if (d != 0) { const ulonglong2 c0 = *A0; m0.x += c0.x; m0.y += c0.y; }
                     *A0 = m0;
                 }
-                if (F1) {
+                if (R1) {
+                    acc1[2 * pj] = __dadd_rn(acc1[2 * pj], fp_mulmod(xd[2 * pj], u2d(k1[j].x), fq, fqinv));
+                    acc1[2 * pj + 1] = __dadd_rn(acc1[2 * pj + 1], fp_mulmod(xd[2 * pj + 1], u2d(k1[j].y), fq, fqinv));
+                } else if (F1) {
                     double2 m1;
                     m1.x = fp_mulmod(xd[2 * pj], u2d(k1[j].x), fq, fqinv); m1.y = fp_mulmod(xd[2 * pj + 1], u2d(k1[j].y), fq, fqinv);
                     double2* A1 = accd + (size_t)(1 * 4 + pj) * T + tid;
@@ -878,7 +882,9 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
             const ulonglong2 c0 = accs[(size_t)(0 * 4 + pj) * T + tid];
             r0.x = bred_add(c0.x, q, L.bred_hi); r0.y = bred_add(c0.y, q, L.bred_hi);
         }
-        if (F1) {
+        if (R1) {
+            r1.x = fp_canon(fp_mulmod(acc1[2 * pj], rinv, fq, fqinv), fq, fqinv); r1.y = fp_canon(fp_mulmod(acc1[2 * pj + 1], rinv, fq, fqinv), fq, fqinv);
+        } else if (F1) {
             const double2 c1 = accd[(size_t)(1 * 4 + pj) * T + tid];
             r1.x = fp_canon(fp_mulmod(c1.x, rinv, fq, fqinv), fq, fqinv); r1.y = fp_canon(fp_mulmod(c1.y, rinv, fq, fqinv), fq, fqinv);
         } else {
@@ -1170,10 +1176,13 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
         if (k3v == 11) {
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ks_chunk_mac_fp8r_kernel<1><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
+        } else if (k3v == 13) {
+            LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ks_chunk_mac_fp8r_kernel<3><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
         } else if (k3v == 12) {
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ks_chunk_mac_fp8r_kernel<2><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
-        } else if (k3v != 0) {
+        } else if (k3v != 0) {      // 10
             LGPU_CUDA_OK(cudaFuncSetAttribute(ks_chunk_mac_fp8r_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ks_chunk_mac_fp8r_kernel<0><<<dim3(batch, chunks, fp.nrows), 512, smem, st>>>(cp);
         } else {
