@@ -206,14 +206,20 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t_end = time.time() + 5.0                      # first line = NVML is up and polling
+            while not self.lines and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples that arrived inside [t0, t1] (host wall clock of the timed region; the poller itself is started BEFORE the warm-up so that its
+        start-up -- NVML initialisation takes driver locks for a few hundred ms -- never overlaps a timed step). A region shorter than the 100 ms
+        polling period keeps the samples nearest to it."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -222,8 +228,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = list(self.lines)
+        if t0 is not None and t1 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1 + 0.12]
+            if len(inside) < 2:
+                inside = sorted(rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+            rows = inside
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        for _, ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -287,22 +299,24 @@ def gpu_main(args):
     def step():
         return ev.MulRelinRescaleNew(a, b)
 
-    for _ in range(args.warmup):
-        out = step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
     l0 = _lib.lib().lgpu_launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.time()
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     barrier()
+    w1 = time.time()
     launches = _lib.lib().lgpu_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
     t_dev = e0.elapsed_time(e1) * 1e-3
     t_max = D.max_over_ranks(t_dev, dev)
     value = D.job_throughput(B * args.steps, t_dev, dev)
@@ -463,16 +477,17 @@ def bootstrap_main(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        rep.run()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        rep.run()
+    barrier()
     l0 = _lib.lib().lgpu_launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     phases = {}
     barrier()
+    w0 = time.time()
     e0.record()
     for _ in range(args.steps):
         ms, nops = rep.run()
@@ -480,8 +495,9 @@ def bootstrap_main(args):
             phases[k] = phases.get(k, 0.0) + v
     e1.record()
     barrier()
+    w1 = time.time()
     launches = _lib.lib().lgpu_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
     from lattigo_b200 import dist as D
     t_max = D.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
     alg = None
