@@ -755,6 +755,12 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
         if (dn == own_d) dn++;
         u64 xv[8];
         double xd[8];
+        // the twiddle addresses are loop-invariant too; left alone the compiler hoists the 12 pointers out of the loop and spills them. Laundering the
+        // base and the thread index makes it recompute them here (a few integer instructions on pipes that are idle) instead of reloading them from
+        // local memory through the L1 that bounds this kernel
+        const double* twl = tw;
+        int tl = tid;
+        asm volatile("" : "+l"(twl), "+r"(tl));
         if (!own) {
             {
                 double x[8];
@@ -765,29 +771,24 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                     if (KS_L2_PREFETCH && dn < p.nd && tid < 256)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(P1row + (size_t)dn * p.p1_ds + tid * 16));
                 }
+                {
+                    double t1[7];
+                    fp8_load_tw<0, true>(t1, twl, s1, chunk, tl);       // CTA-uniform: hi = 0
 #pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)raw[k]);
-#pragma unroll
-                for (int u = 0; u < 3; u++) {
-                    const int half = 4 >> u;
-                    const int twbase = (1 << (s1 + u)) + (chunk << u);
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        if (k & half) continue;
-                        fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), fq, fqinv);
-                    }
+                    for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)raw[k]);
+                    fp8_bflys(x, t1, fq, fqinv);
                 }
                 if (pending) { mbar_wait(bar, tok); pending = false; }
                 fp8s_store_r1(fsm, x, tid);
             }
             double t[7];
-            fp8_load_tw<3>(t, tw, s1, chunk, tid);
+            fp8_load_tw<3, true>(t, twl, s1, chunk, tl);
             __syncthreads();
             fp8s_round2(fsm, t, fq, fqinv, tid);
-            fp8_load_tw<6>(t, tw, s1, chunk, tid);
+            fp8_load_tw<6, true>(t, twl, s1, chunk, tl);
             fp8s_pair_sync(tid);
             fp8s_round3(fsm, t, fq, fqinv, tid);
-            fp8_load_tw<9>(t, tw, s1, chunk, tid);
+            fp8_load_tw<9, true>(t, twl, s1, chunk, tl);
             __syncwarp();
             {   // last round stays in registers: coefficients 8*tid .. 8*tid+7
                 double x[8];
@@ -1307,15 +1308,10 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
         double x[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) x[k] = __longlong_as_double((long long)src[k * T + tid]);
-#pragma unroll
-        for (int u = 0; u < 3; u++) {
-            const int half = 4 >> u;
-            const int twbase = (1 << (s1 + u)) + (chunk << u);
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if (k & half) continue;
-                fp_fwd_bfly(x[k], x[k + half], __ldg(tw + twbase + (k >> (3 - u))), fq, fqinv);
-            }
+        {
+            double t1[7];
+            fp8_load_tw<0>(t1, tw, s1, chunk, tid);       // CTA-uniform: hi = 0
+            fp8_bflys(x, t1, fq, fqinv);
         }
         fp8s_store_r1(fsm, x, tid);
     }

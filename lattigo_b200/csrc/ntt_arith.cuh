@@ -400,16 +400,46 @@ __device__ __forceinline__ void fp_inv_round(double* sm, u64* gdst, const LimbCo
 
 
 // 512-thread x 8-element FP64 rounds (four radix-8 rounds per 4096-element chunk)
-template <int A>
+// The 1 + 2 + 4 twiddles of a radix-8 round are three CONTIGUOUS runs of the table (8, 16 and 32 bytes, aligned to their size: the table is
+// allocated 256-byte aligned and every run starts at a multiple of its length), so they are fetched as one 64-, one 128- and one 256-bit load.
+// In the last round (A = 9, one group per thread) the seven scalar loads touched 2 + 8 + 32 = 42 L1 wavefronts per warp (stride-2 / stride-4
+// 8-byte accesses use a quarter of every sector they pull); the vector loads touch 2 + 4 + 8. ncu on the key-switch MAC kernel showed
+// l1tex__throughput at 86 % of peak, i.e. that kernel is bound by exactly these wavefronts.
+#ifndef LGPU_TW_VEC
+#define LGPU_TW_VEC 1
+#endif
+__device__ __forceinline__ void ldg_f64x4(const double* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+// VOL: the loads are `asm volatile`, i.e. issued where they are written. Inside the digit loop of the key-switch MAC kernel the twiddles are
+// loop-invariant; left to the compiler they are hoisted out of the loop, do not fit in the 64-register budget and come back as local-memory
+// reloads (2 L1 wavefronts per 8-byte LDL against 1 for a CTA-uniform LDG) -- on exactly the unit that bounds that kernel.
+template <int A, bool VOL = false>
 __device__ __forceinline__ void fp8_load_tw(double (&t)[7], const double* tw, int s1, int chunk, int tid) {
     constexpr int LOB = 9 - A;
     const int hi = tid >> LOB;
+#if LGPU_TW_VEC
+    const double* p0 = tw + (1 << (s1 + A)) + (chunk << A) + hi;
+    const double* p1 = tw + (1 << (s1 + A + 1)) + (chunk << (A + 1)) + (hi << 1);
+    const double* p2 = tw + (1 << (s1 + A + 2)) + (chunk << (A + 2)) + (hi << 2);
+    if (VOL) {
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(t[0]) : "l"(p0));
+        asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(t[1]), "=d"(t[2]) : "l"(p1));
+        asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(t[3]), "=d"(t[4]), "=d"(t[5]), "=d"(t[6]) : "l"(p2));
+    } else {
+        t[0] = __ldg(p0);
+        const double2 v = __ldg(reinterpret_cast<const double2*>(p1));
+        t[1] = v.x; t[2] = v.y;
+        ldg_f64x4(p2, t[3], t[4], t[5], t[6]);
+    }
+#else
 #pragma unroll
     for (int u = 0; u < 3; u++) {
         const int twbase = (1 << (s1 + A + u)) + (chunk << (A + u)) + (hi << u);
 #pragma unroll
         for (int m = 0; m < (1 << u); m++) t[(1 << u) - 1 + m] = __ldg(tw + twbase + m);
     }
+#endif
 }
 template <int A>
 __device__ __forceinline__ void fp8_round(double* sm, const double (&t)[7], double q, double qinv, int tid) {

@@ -264,10 +264,7 @@ struct FpFwdOps2 : FpFwdOps<RL, 0> {
         const double fq = L.fq, fqinv = L.fqinv;
         const double* tw = L.ftw_fwd;
         double tt[7];
-#pragma unroll
-        for (int u = 0; u < 3; u++)
-#pragma unroll
-            for (int m = 0; m < (1 << u); m++) tt[(1 << u) - 1 + m] = __ldg(tw + (1 << (s1 + u)) + (chunk << u) + m);
+        fp8_load_tw<0>(tt, tw, s1, chunk, tid);           // CTA-uniform: hi = 0
         double x[8];
         if (SRC == 0) {
 #pragma unroll
