@@ -521,6 +521,7 @@ struct KsChunkParams {
     int nQk;                                // Q rows in the key
     u64* acc; size_t acc_cs, acc_bs;        // [batch][2][nq+np][N]
     int logN, nq, k, nd;
+    int wide;                               // 1: key / own rows are 32-byte aligned -> 256-bit loads in the register-MAC kernels (LGPU_K3_WIDE)
 };
 
 template <bool FP>
@@ -708,6 +709,19 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, u64 tok) {
 __device__ __forceinline__ ulonglong2 ldg128(const u64* p) {
     return KS_STREAM ? __ldcs(reinterpret_cast<const ulonglong2*>(p)) : __ldg(reinterpret_cast<const ulonglong2*>(p));
 }
+// 4 consecutive words in one request. Every thread of the register-MAC kernels reads its own 64 contiguous bytes of a key row, so a warp-wide load
+// touches all 16 lines of a 2 KB span whatever its width: four 128-bit loads cost 4 x 16 tag look-ups in the L1 that bounds the kernel, two 256-bit
+// loads 2 x 16 for the same bytes.
+__device__ __forceinline__ void ldg256(const u64* p, u64& a, u64& b, u64& c, u64& d) {
+    asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+// coherent forms for buffers the same kernel writes (the epilogue's operands may alias its output)
+__device__ __forceinline__ void ld256(const u64* p, u64& a, u64& b, u64& c, u64& d) {
+    asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(u64* p, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" :: "l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 
 // MACV selects the pipe of the multiply-accumulate (LGPU_K3_VARIANT = 10 + MACV):
 //   0  integer pipes: MRedLazy(key, x) with the biased-integer x, u64 sums, one Barrett step at the end;
@@ -806,8 +820,13 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
                 }
             }
         } else {
+            if (p.wide) {
+                ldg256(xin, xv[0], xv[1], xv[2], xv[3]);
+                ldg256(xin + 4, xv[4], xv[5], xv[6], xv[7]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) { const ulonglong2 v = ldg128(xin + 2 * j); xv[2 * j] = v.x; xv[2 * j + 1] = v.y; }
+                for (int j = 0; j < 4; j++) { const ulonglong2 v = ldg128(xin + 2 * j); xv[2 * j] = v.x; xv[2 * j + 1] = v.y; }
+            }
             if (F0) {
                 if ((xv[0] | xv[1] | xv[2] | xv[3] | xv[4] | xv[5] | xv[6] | xv[7]) >> 46) {
 #pragma unroll
@@ -820,8 +839,13 @@ __global__ void __launch_bounds__(512, 2) ks_chunk_mac_fp8r_kernel(KsChunkParams
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             ulonglong2 k0[2], k1[2];
+            if (p.wide) {
+                ldg256(e0 + 4 * h, k0[0].x, k0[0].y, k0[1].x, k0[1].y);
+                ldg256(e1 + 4 * h, k1[0].x, k1[0].y, k1[1].x, k1[1].y);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 2; j++) { k0[j] = ldg128(e0 + 4 * h + 2 * j); k1[j] = ldg128(e1 + 4 * h + 2 * j); }
+                for (int j = 0; j < 2; j++) { k0[j] = ldg128(e0 + 4 * h + 2 * j); k1[j] = ldg128(e1 + 4 * h + 2 * j); }
+            }
             if (F0) {
                 u64 g = k0[0].x | k0[0].y | k0[1].x | k0[1].y;
                 if (F1) g |= k1[0].x | k1[0].y | k1[1].x | k1[1].y;
@@ -1133,6 +1157,10 @@ int gadget_product_multiple_p_fused(const Ctx* c, int levelQ, CSpan cx, CSpan cx
     cp.evk = evk.data; cp.evk_cs = key_rows * N; cp.evk_ds = (size_t)evk.npw2max * 2 * key_rows * N; cp.nQk = evk.levelQ + 1;
     cp.acc = acc; cp.acc_cs = acc_cs; cp.acc_bs = acc_bs;
     cp.logN = c->logN; cp.nq = nq; cp.k = k; cp.nd = nd;
+    // LGPU_K3_WIDE (default 1): 256-bit key / own-row loads when everything is 32-byte aligned (the ABI only asks for 16)
+    static const int k3wide = [] { const char* e = getenv("LGPU_K3_WIDE"); return e ? atoi(e) : 1; }();
+    cp.wide = k3wide && ((reinterpret_cast<uintptr_t>(cp.evk) | reinterpret_cast<uintptr_t>(cp.cx)) & 31u) == 0 &&
+              ((cp.evk_ds | cp.evk_cs | cp.cx_rs | cp.cx_bs) & 3u) == 0;
     const size_t smem = (size_t)(4096 + 256 + 8 + 2 * 4096) * sizeof(u64);
     const unsigned gx = (unsigned)(((N >> s1) + 255) / 256);
     const unsigned chunks = (unsigned)(N >> 12);
@@ -1211,6 +1239,7 @@ struct FzChunkParams {
     const u64* D; size_t d_cs, d_bs;
     u64* out; size_t o_cs, o_bs;
     int nb, logN;
+    int wide;                 // 1: A / D / out are 32-byte aligned -> 256-bit accesses in fz_chunk_epi_fp8_kernel (LGPU_K3_WIDE)
     u64 s[kMaxRows];
 };
 
@@ -1326,24 +1355,42 @@ __global__ void __launch_bounds__(512, 2) fz_chunk_epi_fp8_kernel(FzChunkParams 
     // the operands of the epilogue for this thread's 8 consecutive coefficients (last round: stages 9..11 act inside
     // aligned groups of 8), issued before the warp-level exchange so that their latency overlaps it
     ulonglong2 a[4], d[4];
+    if (p.wide) {
+        ld256(A + 8 * tid, a[0].x, a[0].y, a[1].x, a[1].y);
+        ld256(A + 8 * tid + 4, a[2].x, a[2].y, a[3].x, a[3].y);
+        if (D) {
+            ld256(D + 8 * tid, d[0].x, d[0].y, d[1].x, d[1].y);
+            ld256(D + 8 * tid + 4, d[2].x, d[2].y, d[3].x, d[3].y);
+        } else {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        a[j] = *reinterpret_cast<const ulonglong2*>(A + 8 * tid + 2 * j);
-        d[j] = D ? *reinterpret_cast<const ulonglong2*>(D + 8 * tid + 2 * j) : make_ulonglong2(0, 0);
+            for (int j = 0; j < 4; j++) d[j] = make_ulonglong2(0, 0);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            a[j] = *reinterpret_cast<const ulonglong2*>(A + 8 * tid + 2 * j);
+            d[j] = D ? *reinterpret_cast<const ulonglong2*>(D + 8 * tid + 2 * j) : make_ulonglong2(0, 0);
+        }
     }
     __syncwarp();
     double x[8];
     fp8s_load_r4(fsm, x, tid);
     fp8_bflys(x, t, fq, fqinv);
+    ulonglong2 r[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        ulonglong2 r;
         const u64 xa = KS_LAZY_X ? fp_biased_u64(x[2 * j], off52) : fp_canon(x[2 * j], fq, fqinv);
         const u64 xb = KS_LAZY_X ? fp_biased_u64(x[2 * j + 1], off52) : fp_canon(x[2 * j + 1], fq, fqinv);
-        r.x = mred(xa + twoq - a[j].x, sc, q, qinv);
-        r.y = mred(xb + twoq - a[j].y, sc, q, qinv);
-        if (D) { r.x = cred(r.x + d[j].x, q); r.y = cred(r.y + d[j].y, q); }
-        *reinterpret_cast<ulonglong2*>(out + 8 * tid + 2 * j) = r;
+        r[j].x = mred(xa + twoq - a[j].x, sc, q, qinv);
+        r[j].y = mred(xb + twoq - a[j].y, sc, q, qinv);
+        if (D) { r[j].x = cred(r[j].x + d[j].x, q); r[j].y = cred(r[j].y + d[j].y, q); }
+    }
+    if (p.wide) {
+        st256(out + 8 * tid, r[0].x, r[0].y, r[1].x, r[1].y);
+        st256(out + 8 * tid + 4, r[2].x, r[2].y, r[3].x, r[3].y);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) *reinterpret_cast<ulonglong2*>(out + 8 * tid + 2 * j) = r[j];
     }
 }
 
@@ -1410,7 +1457,11 @@ static int fz_launch_chunk(const FzChunkParams& p, dim3 grid, cudaStream_t st) {
     const bool vec_ok = aligned16(p.A) && aligned16(p.D) && aligned16(p.out) && even_words(p.a_cs, p.a_bs) && even_words(p.d_cs, p.d_bs) &&
                         even_words(p.o_cs, p.o_bs);
     if (FP && v8 == 8 && vec_ok) {
-        fz_chunk_epi_fp8_kernel<<<grid, 512, smem, st>>>(p);
+        static const int k3wide = [] { const char* e = getenv("LGPU_K3_WIDE"); return e ? atoi(e) : 1; }();
+        FzChunkParams pw = p;
+        pw.wide = k3wide && ((reinterpret_cast<uintptr_t>(p.A) | reinterpret_cast<uintptr_t>(p.D) | reinterpret_cast<uintptr_t>(p.out)) & 31u) == 0 &&
+                  ((p.a_cs | p.a_bs | p.d_cs | p.d_bs | p.o_cs | p.o_bs) & 3u) == 0;
+        fz_chunk_epi_fp8_kernel<<<grid, 512, smem, st>>>(pw);
         LGPU_CUDA_OK(cudaGetLastError());
         return 0;
     }
