@@ -14,7 +14,9 @@
  *   - Alignment: lgpu_malloc / cudaMalloc blocks are always fine. The ring-level entry points accept any
  *     8-byte aligned pointer (odd word offsets take 64-bit kernels); the rlwe-level ones (gadget products,
  *     evaluator_*, ckks_*) and evaluation keys require 16-byte aligned blocks and even strides, and return
- *     an error otherwise (their kernels move 128 bits per access).
+ *     an error otherwise (their kernels move 128 bits per access). Keys and ciphertexts that are 32-byte aligned
+ *     (every cudaMalloc / lgpu_malloc block whose rows are a multiple of 4 words apart) additionally take the 256-bit
+ *     accesses of the fused key-switch kernels; results are identical either way.
  *   - `ring` selects the moduli chain: LGPU_RING_Q or LGPU_RING_P (ringqp.Ring{RingQ,RingP},
  *     ring/ringqp/ring.go:15-17). `level` is the reference's level (number of limbs - 1).
  *   - All calls are asynchronous on `stream` (a cudaStream_t cast to void*; NULL = the CUDA default
