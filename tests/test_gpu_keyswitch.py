@@ -518,7 +518,7 @@ def test_unaligned_buffers():
     ctx.close()
 
 
-@pytest.mark.parametrize("env", ["LGPU_K3_VARIANT=0", "LGPU_K3_VARIANT=10", "LGPU_K3_VARIANT=12", "LGPU_K3_VARIANT=13", "LGPU_K2_SPLIT=0", "LGPU_K2_J4=0", "LGPU_FZ_VARIANT=0", "LGPU_NO_FUSED_KS=1", "LGPU_NO_FP64_NTT=1",
+@pytest.mark.parametrize("env", ["LGPU_K3_VARIANT=0", "LGPU_K3_VARIANT=10", "LGPU_K3_VARIANT=12", "LGPU_K3_VARIANT=13", "LGPU_K3_WIDE=0", "LGPU_K2_SPLIT=0", "LGPU_K2_J4=0", "LGPU_FZ_VARIANT=0", "LGPU_NO_FUSED_KS=1", "LGPU_NO_FP64_NTT=1",
                                  "LGPU_SIDE_STREAM=1", "LGPU_BATCH_CHUNK=1"])
 def test_fallback_kernel_variants_stay_bit_exact(env):
     """The development switches select the older / unfused kernels (read once per process, hence a subprocess); every
