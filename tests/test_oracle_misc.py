@@ -45,6 +45,15 @@ def test_mult_by_monomial_is_ntt_multiplication():
         assert np.array_equal(yy, c), k
 
 
+def test_shift_known_answer_of_the_reference():
+    """ring/ring_test.go:906-919 (testShift): NewRing(16, {97}), coefficients 0..15 shifted by 3."""
+    r = O.Ring(16, [97])
+    x = np.arange(16, dtype=U64)[None, :].copy()
+    y = np.zeros_like(x)
+    r.Shift(x, 3, y)
+    assert y[0].tolist() == [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 0, 1, 2]
+
+
 def test_shift_and_extend_basis():
     N = 32
     Q = H.Qi60[:2]; P = H.Pi60[:2]
