@@ -44,3 +44,30 @@ def test_bootstrap_workload_reference_arm_is_declared_unavailable():
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and "unavailable" in line
+
+
+def test_clock_sampler_keeps_the_samples_of_the_timed_region():
+    """ClockSampler.stop(t0, t1): only lines that arrived during the timed region count (the poller runs from before the warm-up);
+    throttle reasons outside it are not reported, reasons inside it are; a region shorter than the polling period keeps the nearest lines."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class FakeProc:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    def line(sm, hw="Not Active", pw="Not Active"):
+        return "0, %d, 1965, 700.0, 0x0, %s, Not Active, Not Active, %s" % (sm, hw, pw)
+
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [(9.0, line(1200, hw="Active")), (10.05, line(1965)), (10.15, line(1950, pw="Active")), (10.25, line(1965)), (11.0, line(900, hw="Active"))]
+    r = s.stop(10.0, 10.3)
+    assert r["samples"] == 3 and r["sm_mhz"] == 1965.0 and r["sm_max_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"]
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.lines = [(9.0, line(1200)), (10.02, line(1965)), (11.0, line(900))]
+    r = s.stop(10.0, 10.01)                       # shorter than the polling period: nearest samples
+    assert r["samples"] == 3 and r["sm_mhz"] == 1200.0
+    assert bench.ClockSampler(0).stop()["reasons"] == ["nvidia-smi unavailable"]
